@@ -1,0 +1,343 @@
+// C[M,N] = epilogue(A[M,K] · W[N,K]^T)   bf16 in, fp32 accumulate in TMEM, bf16 out.   sm_100a only.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled tiles, 4-stage mbarrier ring)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       (tcgen05.ld -> registers -> fused epilogue -> global), double-buffered against the
+//                              next tile's main loop through two TMEM accumulator stages
+// Replaces, on the hot path, every nn.Linear of the reference's denoising step:
+// models/transformer.py:200-221 (attn1.to_q/k/v/to_out, ff), models/router.py:226-228,301-302,430-466,
+// models/audio_model.py:179-185.  The fused epilogues replace the elementwise ops the reference runs after them:
+// bias, GELU, qk-LayerNorm + RoPE (diffusers CogVideoXAttnProcessor2_0), gate * x + residual (transformer.py:247-260),
+// scale * x + residual (transformer.py:832, :936).
+#include "common.cuh"
+#include "gemm.h"
+
+namespace bya {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kStages = 4;
+constexpr int kThreads = 256;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + slack for 1024 B alignment
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using L = GemmSmem<BN>;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.K / BK;
+  constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (m_blk, n_blk): groups of `group_m` row-blocks sweep all column-blocks, so that concurrently running
+  // CTAs share a small set of A and W tiles in L2.
+  auto tile_coord = [&](int t, int& mb, int& nb) {
+    const int gm = p.group_m;
+    const int per_group = gm * num_n;
+    const int g = t / per_group;
+    const int first_m = g * gm;
+    const int rows = min(gm, num_m - first_m);
+    const int r = t - g * per_group;
+    mb = first_m + r % rows;
+    nb = r / rows;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int mb, nb;
+        tile_coord(t, mb, nb);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, mb * BM, kEvictNormal);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, nb * BN, kEvictLast);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+          const uint64_t da = make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_ss(tmem_acc, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int mb, nb;
+      tile_coord(t, mb, nb);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = mb * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + as * BN + (uint32_t(q * 32) << 16);
+      const int col0 = nb * BN;
+
+      if (p.mode == GEMM_EPI_QKV) {
+        // one 64-wide head per iteration: + bias, LayerNorm(64) on q/k heads, RoPE on video rows
+        const bool is_video = row >= p.split_row;
+        const float* cs = p.rope_cos + size_t(max(row - p.split_row, 0)) * 64;
+        const float* sn = p.rope_sin + size_t(max(row - p.split_row, 0)) * 64;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          uint32_t r[64];
+          tmem_ld_x32(taddr + c, r);
+          tmem_ld_x32(taddr + c + 32, r + 32);
+          tmem_ld_wait();
+          const int col = col0 + c;
+          float v[64];
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            float b0 = 0.f, b1 = 0.f;
+            if (p.bias) {
+              uint32_t bb = *reinterpret_cast<const uint32_t*>(p.bias + col + i);
+              b0 = bf16_lo(bb);
+              b1 = bf16_hi(bb);
+            }
+            v[i] = __uint_as_float(r[i]) + b0;
+            v[i + 1] = __uint_as_float(r[i + 1]) + b1;
+          }
+          if (col < p.qk_cols) {
+            const bool is_k = col >= (p.qk_cols >> 1);
+            const __nv_bfloat16* gw = is_k ? p.nk_w : p.nq_w;
+            const __nv_bfloat16* gb = is_k ? p.nk_b : p.nq_b;
+            float mean = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) mean += v[i];
+            mean *= (1.f / 64.f);
+            float var = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) { float d = v[i] - mean; var += d * d; }
+            const float rstd = rsqrtf(var * (1.f / 64.f) + p.ln_eps);
+#pragma unroll
+            for (int i = 0; i < 64; i += 2) {
+              uint32_t ww = *reinterpret_cast<const uint32_t*>(gw + i);
+              uint32_t bb = *reinterpret_cast<const uint32_t*>(gb + i);
+              v[i] = (v[i] - mean) * rstd * bf16_lo(ww) + bf16_lo(bb);
+              v[i + 1] = (v[i + 1] - mean) * rstd * bf16_hi(ww) + bf16_hi(bb);
+            }
+            if (is_video && row_ok) {
+#pragma unroll
+              for (int i = 0; i < 64; i += 4) {
+                const float4 c4 = *reinterpret_cast<const float4*>(cs + i);
+                const float4 s4 = *reinterpret_cast<const float4*>(sn + i);
+                const float x0 = v[i], x1 = v[i + 1], x2 = v[i + 2], x3 = v[i + 3];
+                v[i] = x0 * c4.x - x1 * s4.x;
+                v[i + 1] = x1 * c4.y + x0 * s4.y;
+                v[i + 2] = x2 * c4.z - x3 * s4.z;
+                v[i + 3] = x3 * c4.w + x2 * s4.w;
+              }
+            }
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldc + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+              o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              dst[i] = o;
+            }
+          }
+        }
+      } else {
+        const float* gate = nullptr;
+        float rscale = p.alpha;
+        float bscale = 1.f;
+        if (p.mode == GEMM_EPI_RESIDUAL) {
+          gate = (row < p.split_row) ? p.gate_a : p.gate_b;
+          if (p.row_bias_scale && row_ok) bscale = p.row_bias_scale[row];
+        }
+        constexpr int CH = (BN >= 32) ? 32 : BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += CH) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c, r);
+          tmem_ld_wait();
+          const int col = col0 + c;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float b0 = 0.f, b1 = 0.f;
+            if (p.bias) {
+              uint32_t bb = *reinterpret_cast<const uint32_t*>(p.bias + col + i);
+              b0 = bf16_lo(bb) * bscale;
+              b1 = bf16_hi(bb) * bscale;
+            }
+            v[i] = __uint_as_float(r[i]) + b0;
+            v[i + 1] = __uint_as_float(r[i + 1]) + b1;
+          }
+          if (p.act == GEMM_ACT_GELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+          } else if (p.act == GEMM_ACT_GELU_ERF) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
+          if (!row_ok) continue;
+          if (p.mode == GEMM_EPI_RESIDUAL) {
+            const uint4* rs = reinterpret_cast<const uint4*>(p.resid + size_t(row) * p.ldr + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 x = rs[i];
+              const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = 8 * i + 2 * j;
+                float g0 = rscale, g1 = rscale;
+                if (gate) {
+                  const float2 gg = *reinterpret_cast<const float2*>(gate + col + e);
+                  g0 *= gg.x;
+                  g1 *= gg.y;
+                }
+                v[e] = bf16_lo(xs[j]) + g0 * v[e];
+                v[e + 1] = bf16_hi(xs[j]) + g1 * v[e + 1];
+              }
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldc + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
+            o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            dst[i] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  int rc = bya_host::encode_tmap_bf16(&ta, A, a.K, a.M, uint64_t(lda) * 2, BK, BM);
+  if (rc) return rc;
+  rc = bya_host::encode_tmap_bf16(&tb, W, a.K, a.N, uint64_t(ldw) * 2, BK, BN);
+  if (rc) return rc;
+  auto kern = gemm_bf16_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal) != cudaSuccess)
+      return BYA_ERR_CUDA;
+    attr_set = true;
+  }
+  const int num_tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
+  const int grid = num_tiles < bya_host::num_sms() ? num_tiles : bya_host::num_sms();
+  kern<<<grid, kThreads, GemmSmem<BN>::kTotal, stream>>>(ta, tb, a);
+  return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
+}
+
+}  // namespace bya
+
+extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W, int ldw, const ByaGemmArgs* args) {
+  using namespace bya;
+  if (!A || !W || !args || !args->out) return BYA_ERR_SHAPE;
+  GemmArgs a = *args;
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.K % BK != 0) return BYA_ERR_SHAPE;
+  if (lda % 8 || ldw % 8 || a.ldc % 8 || (a.mode == GEMM_EPI_RESIDUAL && (a.ldr % 8 || !a.resid))) return BYA_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(a.out)) & 15)
+    return BYA_ERR_ALIGN;
+  if (a.group_m <= 0) a.group_m = 16;
+  if (a.mode == GEMM_EPI_QKV) {
+    if (a.N % 64 || a.qk_cols % 128 || !a.rope_cos || !a.rope_sin || !a.nq_w || !a.nq_b || !a.nk_w || !a.nk_b)
+      return BYA_ERR_SHAPE;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a.N % 256 == 0) return launch_gemm<256>(a, A, lda, W, ldw, s);
+  if (a.N % 128 == 0) return launch_gemm<128>(a, A, lda, W, ldw, s);
+  if (a.N % 64 == 0) return launch_gemm<64>(a, A, lda, W, ldw, s);
+  return BYA_ERR_SHAPE;
+}
