@@ -60,3 +60,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
     check(rc, "gemm")
     LAUNCHES += 1
     return out
+
+
+def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, batch: int, seq: int,
+                  heads: int, scale: float = 0.125) -> torch.Tensor:
+    """q/k/v/out: [batch*seq, heads*64] column-slice views (shared row stride for q,k,v) of bf16 matrices."""
+    global LAUNCHES
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _bf16_2d(t, n)
+        if t.shape[0] != batch * seq or t.shape[1] != heads * 64:
+            raise RuntimeError(f"bya_b200.attention_d64: {n} has shape {tuple(t.shape)}")
+    if not (q.stride(0) == k.stride(0) == v.stride(0)):
+        raise RuntimeError("bya_b200.attention_d64: q, k, v must share a row stride")
+    rc = lib().bya_attention_d64(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
+                                 batch, seq, heads, ctypes.c_float(scale))
+    check(rc, "attention_d64")
+    LAUNCHES += 1
+    return out

@@ -63,6 +63,14 @@ typedef struct ByaGemmArgs {
 
 int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W, int ldw, const ByaGemmArgs* args);
 
+/* ---------------------------------------------------------------- multi-head attention, head_dim 64, no mask
+ * out[b*seq+n, h*64..] = softmax(Q_h K_h^T * scale) V_h ; q/k/v/out are row-major [batch*seq, ld] views whose head h
+ * lives at columns [h*64, h*64+64) (i.e. column slices of the fused projection output).
+ * Replaces F.scaled_dot_product_attention inside diffusers CogVideoXAttnProcessor2_0 (transformer.py:241-245) and
+ * inside the router's spatial attention (router.py:474-476). */
+int bya_attention_d64(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo,
+                      int batch, int seq, int heads, float scale);
+
 #ifdef __cplusplus
 }
 #endif

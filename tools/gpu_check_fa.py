@@ -1,0 +1,56 @@
+"""GPU check of the tcgen05 flash attention against torch SDPA (run on the B200 box through gpurun)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+import bya_b200
+from bya_b200 import ops
+
+torch.manual_seed(0)
+dev = "cuda"
+
+def run(batch, seq, heads, qscale=1.0, check=True, iters=0):
+    D = heads * 64
+    qkv = (torch.randn(batch * seq, 3 * D, device=dev) * qscale).bfloat16()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    out = torch.zeros(batch * seq, D, device=dev, dtype=torch.bfloat16)
+    ops.attention_d64(q, k, v, out, batch, seq, heads)
+    torch.cuda.synchronize()
+    ok = True
+    if check:
+        def hv(x): return x.reshape(batch, seq, heads, 64).transpose(1, 2).float()
+        ref = F.scaled_dot_product_attention(hv(q), hv(k), hv(v)).transpose(1, 2).reshape(batch * seq, D)
+        err = (out.float() - ref).abs().max().item()
+        rel = err / ref.abs().max().item()
+        ok = rel < 2e-2 and bool(torch.isfinite(out.float()).all())
+        print(f"fa batch={batch} seq={seq} heads={heads} qscale={qscale}: max_abs={err:.3e} rel={rel:.3e}", "OK" if ok else "FAIL", flush=True)
+    if iters:
+        for _ in range(2): ops.attention_d64(q, k, v, out, batch, seq, heads)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); s.record()
+        for _ in range(iters): ops.attention_d64(q, k, v, out, batch, seq, heads)
+        e.record(); torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / iters
+        fl = 4.0 * batch * heads * seq * seq * 64 / 1e9
+        def hb(x): return x.reshape(batch, seq, heads, 64).transpose(1, 2)
+        for _ in range(2): F.scaled_dot_product_attention(hb(q), hb(k), hb(v))
+        torch.cuda.synchronize(); s.record()
+        for _ in range(iters): F.scaled_dot_product_attention(hb(q), hb(k), hb(v))
+        e.record(); torch.cuda.synchronize()
+        ms2 = s.elapsed_time(e) / iters
+        print(f"bench fa batch={batch} seq={seq} heads={heads}: bya {ms:.3f} ms = {fl/ms:.0f} TF/s | torch sdpa {ms2:.3f} ms = {fl/ms2:.0f} TF/s", flush=True)
+    return ok
+
+ok = True
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "small"):
+    ok &= run(1, 128, 1)
+    ok &= run(1, 256, 2)
+    ok &= run(1, 512, 4)
+    ok &= run(1, 1000, 3)
+    ok &= run(2, 1350, 8)
+    ok &= run(1, 1474, 48, qscale=3.0)
+if which in ("all", "big"):
+    ok &= run(1, 17776, 48, iters=5)
+    run(26, 1350, 8, check=False, iters=10)
+print("ALL OK" if ok else "SOME FAILED")
