@@ -1,0 +1,270 @@
+// Routed per-character cross-attention with 32 keys per (character, frame), and the router's tiny strided
+// self-attentions.   sm_100a build; warp-level mma.sync tiles (the problem is 32 keys wide — far below a tcgen05
+// tile — and HBM/latency bound: q is read once, the blended result written once).
+//
+//   out[n, h*d : (h+1)*d] = sum_c w[n,c] * softmax_k(scale * q[n,h,:] . K[g(c,n)][h][k][:]) @ V[g(c,n)][h]
+//   g(c, n) = c * kv_frames + n / tokens_per_frame
+// i.e. the per-character attention AND the routed blend of models/transformer.py:821-822 / :925-926 in one pass:
+// each token gathers only the K/V of its own frame, and the per-character results are never materialised
+// (blend-then-project).  Replaces the attention core of
+// PerceiverCrossAttention.forward (models/router.py:256-273; softmax in fp32) and of the audio cross-attention
+// (models/audio_model.py:253-256 -> diffusers AttnProcessor2_0).
+#include "common.cuh"
+#include "../../include/bya.h"
+
+namespace bya {
+
+BYA_DEVICE void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int XA_WARPS = 8;
+constexpr int XA_TOK = XA_WARPS * 16;  // tokens per block
+
+// K  : [G][H][32][D]   (keys x head-dim, head-dim contiguous)
+// Vt : [G][H][D][32]   (V transposed: head-dim x keys, keys contiguous)  — both prepared once per generation
+template <int D, int C>
+__global__ void __launch_bounds__(XA_WARPS * 32)
+xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ K,
+                  const __nv_bfloat16* __restrict__ Vt, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                  int ldo, int heads, int tokens_per_frame, int kv_frames, float scale_log2) {
+  constexpr int KP = D + 8;    // padded row of the K tile (bank-conflict-free fragment loads)
+  constexpr int VP = 32 + 8;   // padded row of the V^T tile
+  extern __shared__ __align__(16) uint8_t xa_smem[];
+  typedef __nv_bfloat16 (*KTile)[32][KP];
+  typedef __nv_bfloat16 (*VTile)[D][VP];
+  KTile sK = reinterpret_cast<KTile>(xa_smem);
+  VTile sV = reinterpret_cast<VTile>(xa_smem + size_t(C) * 32 * KP * 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int frame = blockIdx.y;
+  const int tok0 = blockIdx.x * XA_TOK + warp * 16;               // within the frame
+  const int r0 = tok0 + g, r1 = tok0 + g + 8;                     // this thread's two rows (within the frame)
+  const bool ok0 = r0 < tokens_per_frame, ok1 = r1 < tokens_per_frame;
+  const size_t n0 = size_t(frame) * tokens_per_frame + r0, n1 = size_t(frame) * tokens_per_frame + r1;
+
+  float wt0[C], wt1[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    wt0[c] = (w && ok0) ? w[n0 * C + c] : 1.f;
+    wt1[c] = (w && ok1) ? w[n1 * C + c] : 1.f;
+  }
+
+  for (int h = 0; h < heads; ++h) {
+    __syncthreads();
+    // ---- stage K_h and V^T_h of every character (this block's frame) in shared memory
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const size_t grp = (size_t(c) * kv_frames + frame) * heads + h;
+      const uint4* gk = reinterpret_cast<const uint4*>(K + grp * 32 * D);
+      for (int i = threadIdx.x; i < 32 * D / 8; i += blockDim.x) {
+        const int row = i / (D / 8), cc = i % (D / 8);
+        *reinterpret_cast<uint4*>(&sK[c][row][cc * 8]) = gk[i];
+      }
+      const uint4* gv = reinterpret_cast<const uint4*>(Vt + grp * 32 * D);
+      for (int i = threadIdx.x; i < D * 32 / 8; i += blockDim.x) {
+        const int row = i / 4, cc = i % 4;
+        *reinterpret_cast<uint4*>(&sV[c][row][cc * 8]) = gv[i];
+      }
+    }
+    __syncthreads();
+
+    // ---- Q fragments of this warp's 16 tokens for head h (straight from global; zero for rows past the frame)
+    uint32_t qa[D / 16][4];
+    const __nv_bfloat16* q0 = q + n0 * ldq + h * D;
+    const __nv_bfloat16* q1 = q + n1 * ldq + h * D;
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      qa[kk][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 2 * t) : 0u;
+      qa[kk][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 2 * t) : 0u;
+      qa[kk][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 8 + 2 * t) : 0u;
+      qa[kk][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 8 + 2 * t) : 0u;
+    }
+
+    float o[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      // S = Q K_c^T : 16 x 32
+      float s[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[c][nt * 8 + g][kk * 16 + 2 * t]);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[c][nt * 8 + g][kk * 16 + 8 + 2 * t]);
+          mma_bf16_16816(s[nt], qa[kk], b0, b1);
+        }
+      }
+      // softmax over the 32 keys of character c (rows g and g+8), fp32
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        s[nt][0] = exp2f((s[nt][0] - m0) * scale_log2);
+        s[nt][1] = exp2f((s[nt][1] - m0) * scale_log2);
+        s[nt][2] = exp2f((s[nt][2] - m1) * scale_log2);
+        s[nt][3] = exp2f((s[nt][3] - m1) * scale_log2);
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float f0 = wt0[c] / l0, f1 = wt1[c] / l1;
+      // O += (w_c * P_c) V_c
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0] * f0, s[2 * kk][1] * f0);
+        pa[1] = pack_bf16x2(s[2 * kk][2] * f1, s[2 * kk][3] * f1);
+        pa[2] = pack_bf16x2(s[2 * kk + 1][0] * f0, s[2 * kk + 1][1] * f0);
+        pa[3] = pack_bf16x2(s[2 * kk + 1][2] * f1, s[2 * kk + 1][3] * f1);
+#pragma unroll
+        for (int nt = 0; nt < D / 8; ++nt) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sV[c][nt * 8 + g][kk * 16 + 2 * t]);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sV[c][nt * 8 + g][kk * 16 + 8 + 2 * t]);
+          mma_bf16_16816(o[nt], pa, b0, b1);
+        }
+      }
+    }
+    // ---- store
+    __nv_bfloat16* d0 = out + n0 * ldo + h * D;
+    __nv_bfloat16* d1 = out + n1 * ldo + h * D;
+#pragma unroll
+    for (int nt = 0; nt < D / 8; ++nt) {
+      if (ok0) *reinterpret_cast<uint32_t*>(d0 + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0], o[nt][1]);
+      if (ok1) *reinterpret_cast<uint32_t*>(d1 + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2], o[nt][3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Router temporal (L = frames) and multi-ID (L = characters) self-attention, 8 heads x 64 (router.py:478-488).
+// A "sequence" is L rows of the [rows, 3*HD] qkv matrix spaced `tok_stride` rows apart, starting at
+//   base(s) = (s / inner) * outer_stride + (s % inner).
+// One warp per (sequence, head); lanes hold 2 of the 64 head dims; L <= 32.
+template <int MAXL>
+__global__ void __launch_bounds__(256)
+small_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, __nv_bfloat16* __restrict__ out, int ldo,
+                       int n_seq, int L, int heads, int inner, long long outer_stride, long long tok_stride,
+                       float scale) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_seq * heads) return;
+  const int s = warp / heads, h = warp % heads;
+  const long long base = (long long)(s / inner) * outer_stride + (s % inner);
+  const int HD = heads * 64;
+  float2 kx[MAXL], vx[MAXL];
+#pragma unroll
+  for (int j = 0; j < MAXL; ++j) {
+    if (j < L) {
+      const __nv_bfloat16* row = qkv + size_t(base + j * tok_stride) * ld + h * 64 + 2 * lane;
+      const uint32_t ku = *reinterpret_cast<const uint32_t*>(row + HD);
+      const uint32_t vu = *reinterpret_cast<const uint32_t*>(row + 2 * HD);
+      kx[j] = make_float2(bf16_lo(ku), bf16_hi(ku));
+      vx[j] = make_float2(bf16_lo(vu), bf16_hi(vu));
+    }
+  }
+  for (int i = 0; i < L; ++i) {
+    const __nv_bfloat16* row = qkv + size_t(base + i * tok_stride) * ld + h * 64 + 2 * lane;
+    const uint32_t qu = *reinterpret_cast<const uint32_t*>(row);
+    const float q0 = bf16_lo(qu) * scale, q1 = bf16_hi(qu) * scale;
+    float sc[MAXL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j) {
+      if (j < L) {
+        sc[j] = warp_sum(q0 * kx[j].x + q1 * kx[j].y);
+        mx = fmaxf(mx, sc[j]);
+      }
+    }
+    float den = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j) {
+      if (j < L) {
+        const float pj = __expf(sc[j] - mx);
+        den += pj;
+        a0 += pj * vx[j].x;
+        a1 += pj * vx[j].y;
+      }
+    }
+    const float inv = 1.f / den;
+    *reinterpret_cast<uint32_t*>(out + size_t(base + i * tok_stride) * ldo + h * 64 + 2 * lane) =
+        pack_bf16x2(a0 * inv, a1 * inv);
+  }
+}
+
+}  // namespace bya
+
+using namespace bya;
+
+extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* K, const void* Vt, const float* w,
+                              void* out, int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames,
+                              float scale) {
+  if (!q || !K || !Vt || !out || tokens <= 0 || heads <= 0 || kv_frames <= 0 || tokens % kv_frames) return BYA_ERR_SHAPE;
+  if (ldq % 2 || ldo % 2) return BYA_ERR_ALIGN;
+  const int tpf = tokens / kv_frames;
+  dim3 grid((tpf + XA_TOK - 1) / XA_TOK, kv_frames);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const float sl2 = scale * 1.4426950408889634f;
+#define BYA_XA(D_, C_)                                                                                            \
+  do {                                                                                                            \
+    constexpr int smem = C_ * 32 * (D_ + 8) * 2 + C_ * D_ * 40 * 2;                                               \
+    static bool attr = false;                                                                                     \
+    if (!attr) {                                                                                                  \
+      if (cudaFuncSetAttribute(xattn_kv32_kernel<D_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=   \
+          cudaSuccess)                                                                                            \
+        return BYA_ERR_CUDA;                                                                                      \
+      attr = true;                                                                                                \
+    }                                                                                                             \
+    xattn_kv32_kernel<D_, C_><<<grid, XA_WARPS * 32, smem, s>>>(                                                  \
+        (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)K, (const __nv_bfloat16*)Vt, w, (__nv_bfloat16*)out,  \
+        ldo, heads, tpf, kv_frames, sl2);                                                                         \
+  } while (0)
+  if (head_dim == 64 && chars == 1) BYA_XA(64, 1);
+  else if (head_dim == 64 && chars == 2) BYA_XA(64, 2);
+  else if (head_dim == 64 && chars == 3) BYA_XA(64, 3);
+  else if (head_dim == 128 && chars == 1) BYA_XA(128, 1);
+  else if (head_dim == 128 && chars == 2) BYA_XA(128, 2);
+  else if (head_dim == 128 && chars == 3) BYA_XA(128, 3);
+  else return BYA_ERR_SHAPE;
+#undef BYA_XA
+  return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
+}
+
+extern "C" int bya_small_attention(void* stream, const void* qkv, int ld, void* out, int ldo, int n_seq, int seq_len,
+                                   int heads, int inner, long long outer_stride, long long tok_stride, float scale) {
+  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || seq_len > 32 || heads <= 0 || inner <= 0) return BYA_ERR_SHAPE;
+  if (ld % 2 || ldo % 2) return BYA_ERR_ALIGN;
+  const long long warps = (long long)n_seq * heads;
+  const int blocks = int((warps + 7) / 8);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (seq_len <= 4)
+    small_attention_kernel<4><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq, seq_len,
+                                                     heads, inner, outer_stride, tok_stride, scale);
+  else if (seq_len <= 16)
+    small_attention_kernel<16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq,
+                                                      seq_len, heads, inner, outer_stride, tok_stride, scale);
+  else
+    small_attention_kernel<32><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq,
+                                                      seq_len, heads, inner, outer_stride, tok_stride, scale);
+  return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
+}

@@ -1,0 +1,407 @@
+"""The denoising-step engine: packs the model's weights once for the sm_100a kernels and runs one step.
+
+What one step launches (per CFG batch element; SURVEY.md §3.3/§3.4, reference models/transformer.py:615-964):
+
+  temb          timestep_features -> gemv(linear_1, SiLU) -> gemv(linear_2) -> ONE gemv over all 2L+1 adaLN linears
+  embed         text GEMM; patchify -> GEMM (the k=2,s=2 conv as [Nv,192]x[192,D])
+  per layer     LN+modulate -> QKV GEMM (bias + qk-LayerNorm + RoPE epilogue) -> tcgen05 flash attention ->
+                out GEMM (gate*x + residual epilogue) -> LN+modulate -> FFN1 GEMM (GELU epilogue) -> FFN2 GEMM (gated
+                residual epilogue)
+  face layers   LN -> to_q GEMM (once, not per character: §0.11) -> [router | forced masks] -> routed 32-key
+                cross-attention that blends the characters on the fly -> ONE to_out GEMM (scale*x + residual)
+  router        LN(perm-folded) -> to_q GEMM -> score GEMM against block-structured keys -> LN+pos-emb ->
+                4 x {spatial FA, temporal attn, multi-ID attn, MLP} -> head
+  audio layers  audio weights -> LN -> to_q GEMM -> routed per-frame 32-key cross-attention -> to_out GEMM
+  head          LN -> LN+modulate -> proj_out GEMM -> unpatchify
+
+Everything timestep-invariant (face tokens, face K/V, router keys, audio context, audio K/V) is computed once per
+generation in `prologue()` with torch on the GPU and cached.
+There is no fallback path: every op above is a libbya.so kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+
+def _bf(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def router_feature_perm(heads: int = 16, dh: int = 128, device=None) -> torch.Tensor:
+    """f(g): position in the reference's router feature order (d*heads + h) of natural feature g = h*dh + d
+    (router.py:375-378)."""
+    g = torch.arange(heads * dh, device=device)
+    return (g % dh) * heads + g // dh
+
+
+class RouterPack:
+    """Router weights in kernel layout (input permutation folded into norm_q / to_q, QKV fused per attention)."""
+
+    def __init__(self, router):
+        dev = router.norm.weight.device
+        perm = router_feature_perm(router.heads, 2048 // router.heads, dev)
+        self.eps = router.norm.eps
+        self.nq_w, self.nq_b = _bf(router.norm_q.weight[perm]), _bf(router.norm_q.bias[perm])
+        self.to_q = [_bf(l.weight[:, perm]) for l in router.to_q]
+        self.n_w, self.n_b = _bf(router.norm.weight), _bf(router.norm.bias)
+        self.pos = _bf(router.pos_emb.reshape(-1, router.pos_emb.shape[-1]))
+        self.blocks = []
+        for blk in router.spatial_temporal_layers:
+            d = {}
+            for name, attn in (("s", blk.spatial_attn), ("t", blk.temporal_attn), ("i", blk.multi_id_attn)):
+                d[f"{name}_qkv_w"] = _bf(torch.cat([attn.to_q.weight, attn.to_k.weight, attn.to_v.weight], 0))
+                d[f"{name}_qkv_b"] = _bf(torch.cat([attn.to_q.bias, attn.to_k.bias, attn.to_v.bias], 0))
+                d[f"{name}_o_w"], d[f"{name}_o_b"] = _bf(attn.to_out[0].weight), _bf(attn.to_out[0].bias)
+            for k, n in (("n1", blk.norm1), ("n2", blk.norm2), ("n3", blk.norm3), ("n4", blk.norm4)):
+                d[k] = (_bf(n.weight), _bf(n.bias), n.eps)
+            d["m0_w"], d["m0_b"] = _bf(blk.mlp[0].weight), _bf(blk.mlp[0].bias)
+            d["m2_w"], d["m2_b"] = _bf(blk.mlp[2].weight), _bf(blk.mlp[2].bias)
+            self.blocks.append(d)
+        self.head_w, self.head_b = _bf(router.final_proj[0].weight.reshape(-1)), _bf(router.final_proj[0].bias)
+
+
+class _Workspace:
+    """Named scratch buffers, allocated once per geometry (the C ABI never allocates)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name, shape, dtype=torch.bfloat16):
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, device=self.device, dtype=dtype)
+            self.bufs[name] = t
+        return t
+
+
+def run_router(rp: RouterPack, ws: _Workspace, qf: torch.Tensor, kmat: torch.Tensor, layer: int, chars: int, frames: int,
+               hw: int, out: torch.Tensor) -> torch.Tensor:
+    """qf [Nv,2048] (natural head-major face queries) , kmat [C*512,2048] -> out [Nv,C] fp32 soft routing.
+    MultiIPRouter.forward (router.py:364-411) + SpatialTemporalAttentionBlock.forward (:468-493)."""
+    Nv = qf.shape[0]
+    C, M = chars, chars * Nv
+    rq = ws.get("r_q", (Nv, 2048))
+    ops.layernorm_modulate(qf, rq, eps=rp.eps, gamma=rp.nq_w, beta=rp.nq_b)
+    rq2 = ws.get("r_q2", (Nv, 2048))
+    ops.gemm(rq, rp.to_q[layer], rq2)
+    sc = ws.get("r_scores", (Nv, C * 512))
+    ops.gemm(rq2, kmat, sc)
+    x = ws.get("r_x", (M, 512))
+    for c in range(C):
+        ops.layernorm_modulate(sc[:, c * 512:(c + 1) * 512], x[c * Nv:(c + 1) * Nv], eps=rp.eps, gamma=rp.n_w,
+                               beta=rp.n_b, add=rp.pos)
+    xn = ws.get("r_xn", (M, 512))
+    qkv = ws.get("r_qkv", (M, 1536))
+    att = ws.get("r_att", (M, 512))
+    for d in rp.blocks:
+        # spatial: all H*W tokens of one (character, frame)
+        ops.layernorm_modulate(x, xn, eps=d["n1"][2], gamma=d["n1"][0], beta=d["n1"][1])
+        ops.gemm(xn, d["s_qkv_w"], qkv, bias=d["s_qkv_b"])
+        ops.attention_d64(qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:], att, C * frames, hw, 8)
+        ops.gemm(att, d["s_o_w"], x, bias=d["s_o_b"], mode=ops.EPI_RESIDUAL, resid=x)
+        # temporal: the F tokens at one (character, h, w)
+        ops.layernorm_modulate(x, xn, eps=d["n2"][2], gamma=d["n2"][0], beta=d["n2"][1])
+        ops.gemm(xn, d["t_qkv_w"], qkv, bias=d["t_qkv_b"])
+        ops.small_attention(qkv, att, C * hw, frames, 8, hw, Nv, hw)
+        ops.gemm(att, d["t_o_w"], x, bias=d["t_o_b"], mode=ops.EPI_RESIDUAL, resid=x)
+        # multi-ID: the C tokens at one (t, h, w)
+        ops.layernorm_modulate(x, xn, eps=d["n3"][2], gamma=d["n3"][0], beta=d["n3"][1])
+        ops.gemm(xn, d["i_qkv_w"], qkv, bias=d["i_qkv_b"])
+        ops.small_attention(qkv, att, Nv, C, 8, Nv, 0, Nv)
+        ops.gemm(att, d["i_o_w"], x, bias=d["i_o_b"], mode=ops.EPI_RESIDUAL, resid=x)
+        # MLP (exact-erf GELU, ratio 1)
+        ops.layernorm_modulate(x, xn, eps=d["n4"][2], gamma=d["n4"][0], beta=d["n4"][1])
+        ops.gemm(xn, d["m0_w"], att, bias=d["m0_b"], act=ops.ACT_GELU_ERF)
+        ops.gemm(att, d["m2_w"], x, bias=d["m2_b"], mode=ops.EPI_RESIDUAL, resid=x)
+    ops.router_head(x, rp.head_w, rp.head_b, out, Nv, C)
+    return out
+
+
+def router_forward_standalone(router, q_out, k_out, layer_idx):
+    """Module-level entry (`MultiIPRouter.forward` signature): q_out [C,16,Nv,128] -> [1,Nv,C]."""
+    C = k_out.shape[0]
+    Nv = q_out.shape[2]
+    rp = RouterPack(router)
+    ws = _Workspace(q_out.device)
+    qf = q_out[0].transpose(0, 1).reshape(Nv, -1).to(torch.bfloat16).contiguous()  # q is identical for every character
+    kmat = _bf(router.router_keys(k_out.to(router.norm_k.weight.dtype), layer_idx))
+    out = torch.empty(Nv, C, device=q_out.device, dtype=torch.float32)
+    hw = router.height * router.width
+    run_router(rp, ws, qf, kmat, layer_idx, C, router.frames, hw, out)
+    return out[None].to(q_out.dtype)
+
+
+class StepEngine:
+    def __init__(self, model):
+        self.model = model
+        cfg = model.config
+        p = next(model.transformer_blocks.parameters())
+        if p.device.type != "cuda" or p.dtype != torch.bfloat16:
+            raise RuntimeError("bya_b200: the denoiser must live on a CUDA device in bfloat16 "
+                               "(`model.to('cuda', torch.bfloat16)`); there is no CPU path")
+        ops.lib()  # fail loudly if libbya.so is missing
+        self.device = p.device
+        self.D = cfg.num_attention_heads * cfg.attention_head_dim
+        self.heads = cfg.num_attention_heads
+        if cfg.attention_head_dim != 64:
+            raise RuntimeError("bya_b200: attention_head_dim must be 64")
+        self.L = cfg.num_layers
+        self.ws = _Workspace(self.device)
+        self._pack()
+        self._prologue_key = None
+        self._prologue = None
+
+    # ------------------------------------------------------------------------------------------------ packing
+    def _pack(self):
+        m, D = self.model, self.D
+        self.layers = []
+        ada_w, ada_b = [], []
+        for blk in m.transformer_blocks:
+            a = blk.attn1
+            self.layers.append(dict(
+                w_qkv=_bf(torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight], 0)),
+                b_qkv=_bf(torch.cat([a.to_q.bias, a.to_k.bias, a.to_v.bias], 0)) if a.to_q.bias is not None else None,
+                nq=(_bf(a.norm_q.weight), _bf(a.norm_q.bias)), nk=(_bf(a.norm_k.weight), _bf(a.norm_k.bias)),
+                qk_eps=a.norm_q.eps,
+                w_o=_bf(a.to_out[0].weight), b_o=_bf(a.to_out[0].bias),
+                w_f1=_bf(blk.ff.net[0].proj.weight), b_f1=_bf(blk.ff.net[0].proj.bias),
+                w_f2=_bf(blk.ff.net[2].weight), b_f2=_bf(blk.ff.net[2].bias),
+                ln1=(_bf(blk.norm1.norm.weight), _bf(blk.norm1.norm.bias), blk.norm1.norm.eps),
+                ln2=(_bf(blk.norm2.norm.weight), _bf(blk.norm2.norm.bias), blk.norm2.norm.eps),
+            ))
+            for n in (blk.norm1, blk.norm2):
+                ada_w.append(n.linear.weight)
+                ada_b.append(n.linear.bias)
+        ada_w.append(m.norm_out.linear.weight)
+        ada_b.append(m.norm_out.linear.bias)
+        self.ada_w, self.ada_b = _bf(torch.cat(ada_w, 0)), _bf(torch.cat(ada_b, 0))
+        self.te = (_bf(m.time_embedding.linear_1.weight), _bf(m.time_embedding.linear_1.bias),
+                   _bf(m.time_embedding.linear_2.weight), _bf(m.time_embedding.linear_2.bias))
+        pw = m.patch_embed.proj.weight
+        kp = pw[0].numel()
+        self.patch_k = (kp + 63) // 64 * 64
+        w = torch.zeros(D, self.patch_k, device=self.device, dtype=torch.bfloat16)
+        w[:, :kp] = pw.reshape(D, kp)
+        self.patch_w, self.patch_b = w, _bf(m.patch_embed.proj.bias)
+        self.text_w, self.text_b = _bf(m.patch_embed.text_proj.weight), _bf(m.patch_embed.text_proj.bias)
+        self.nf = (_bf(m.norm_final.weight), _bf(m.norm_final.bias), m.norm_final.eps)
+        self.no = (_bf(m.norm_out.norm.weight), _bf(m.norm_out.norm.bias), m.norm_out.norm.eps)
+        po = m.proj_out.weight
+        self.out_cols = po.shape[0]
+        n_pad = (self.out_cols + 63) // 64 * 64
+        self.proj_w = torch.zeros(n_pad, D, device=self.device, dtype=torch.bfloat16)
+        self.proj_w[: self.out_cols] = po
+        self.proj_b = torch.zeros(n_pad, device=self.device, dtype=torch.bfloat16)
+        self.proj_b[: self.out_cols] = m.proj_out.bias
+        self.face = []
+        if m.is_train_face:
+            for ca in m.perceiver_cross_attention:
+                self.face.append(dict(ln=(_bf(ca.norm2.weight), _bf(ca.norm2.bias), ca.norm2.eps), w_q=_bf(ca.to_q.weight),
+                                      w_o=_bf(ca.to_out.weight)))
+            self.router = RouterPack(m.router)
+        self.audio = []
+        if getattr(m, "is_train_audio", False):
+            for lyr in m.audio_model.layers:
+                a = lyr["attn"]
+                self.audio.append(dict(ln=(_bf(lyr["norm_q"].weight), _bf(lyr["norm_q"].bias), lyr["norm_q"].eps),
+                                       w_q=_bf(a.to_q.weight), b_q=_bf(a.to_q.bias), w_o=_bf(a.to_out[0].weight),
+                                       b_o=_bf(a.to_out[0].bias)))
+
+    # ------------------------------------------------------------------------------------------------ prologue
+    @torch.no_grad()
+    def prologue(self, id_cond, id_vit_hidden, audio_embeds, frames, use_router: bool):
+        """Timestep-invariant tensors of one generation; torch on the GPU, once per video."""
+        m = self.model
+        dt = torch.bfloat16
+        C = len(id_cond)
+        B = id_cond[0].shape[0]
+        out = dict(face_k=[], face_vt=[], kmat=[], aud_k=[], aud_vt=[])
+        face = torch.stack([m.local_facial_extractor(id_cond[c].to(self.device, dt),
+                                                     [v.to(self.device, dt) for v in id_vit_hidden[c]]) for c in range(C)], 1)
+        out["face_tokens"] = face  # [B,C,32,2048]
+        for b in range(B):
+            fk, fv, km = [], [], []
+            for j, ca in enumerate(m.perceiver_cross_attention):
+                k, v = ca.face_kv(face[b])
+                fk.append(k)
+                fv.append(v.transpose(-1, -2).contiguous())
+                km.append(m.router.router_keys(k, j) if use_router else None)
+            out["face_k"].append(fk)
+            out["face_vt"].append(fv)
+            out["kmat"].append(km)
+        if audio_embeds is not None and getattr(m, "is_train_audio", False):
+            a = audio_embeds.to(self.device, dt)
+            if a.ndim != 5:
+                raise NotImplementedError("bya_b200: the single-speaker + mute-audio path (audio_embeds.ndim == 4) needs "
+                                          "tests/input/ae_mute.pt, which the reference does not ship (audio_model.py:203)")
+            a = a.reshape(B * C, *a.shape[2:])
+            ctx = m.audio_model.proj_in(m.audio_model.sliding_windows(a, frames)).reshape(B, C, frames, 32, -1)
+            out["audio_ctx"] = ctx
+            for b in range(B):
+                ks, vs = [], []
+                for l in range(len(m.audio_model.layers)):
+                    k, vt = m.audio_model.audio_kv(ctx[b], l)
+                    ks.append(k)
+                    vs.append(vt)
+                out["aud_k"].append(ks)
+                out["aud_vt"].append(vs)
+        return out
+
+    # ------------------------------------------------------------------------------------------------ one step
+    @torch.no_grad()
+    def step(self, hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,
+             audio_embeds, af_matrix, routing_logits_forcing=None, per_frame_forcing=False, cache_prologue=True,
+             taps: Optional[dict] = None):
+        m, cfg, D, ws = self.model, self.model.config, self.D, self.ws
+        dev, bf = self.device, torch.bfloat16
+        B, Fr, Cin, Hl, Wl = hidden_states.shape
+        p = cfg.patch_size
+        gh, gw = Hl // p, Wl // p
+        hw = gh * gw
+        Nv = Fr * hw
+        T = encoder_hidden_states.shape[1]
+        N = T + Nv
+        C = len(id_cond)
+        use_router = routing_logits_forcing is None
+        has_audio = audio_embeds is not None and len(self.audio) > 0
+        tap = (lambda k, v: taps.__setitem__(k, v.detach().float().cpu().clone())) if taps is not None else None
+        if m.is_train_face:
+            m.router.set_grid(Fr, gh, gw)
+            if self.router.pos.shape[0] != Nv:
+                self.router = RouterPack(m.router)
+
+        # ---- prologue (cached per generation)
+        key = None
+        if cache_prologue:
+            ts = list(id_cond) + [v for l in id_vit_hidden for v in l] + ([audio_embeds] if audio_embeds is not None else [])
+            key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts) + (Fr, use_router)
+        if key is None or key != self._prologue_key:
+            self._prologue = self.prologue(id_cond, id_vit_hidden, audio_embeds, Fr, use_router)
+            self._prologue_key = key
+        pro = self._prologue
+        if tap:
+            tap("face_tokens", pro["face_tokens"])
+            if has_audio:
+                tap("audio_ctx", pro["audio_ctx"])
+
+        # ---- conditioning vectors
+        ts_ = timestep.to(dev)
+        if ts_.ndim == 0:
+            ts_ = ts_[None].expand(B)
+        ts_ = ts_.to(torch.int64).contiguous()
+        tf = ws.get("t_feat", (B, D), torch.float32)
+        ops.timestep_features(ts_, tf)
+        t1 = ws.get("t_h", (B, cfg.time_embed_dim), torch.float32)
+        ops.gemv(self.te[0], self.te[1], tf, t1, out_act=1)
+        temb = ws.get("temb", (B, cfg.time_embed_dim), torch.float32)
+        ops.gemv(self.te[2], self.te[3], t1, temb)
+        ada = ws.get("ada", (B, self.ada_w.shape[0]), torch.float32)
+        ops.gemv(self.ada_w, self.ada_b, temb, ada, in_act=1)
+        if tap:
+            tap("temb", temb)
+
+        cos, sin = (t.to(dev, torch.float32).contiguous() for t in image_rotary_emb)
+        forced = None
+        if not use_router:
+            forced = routing_logits_forcing.to(dev, torch.float32).reshape(Nv, C).contiguous()
+            if not per_frame_forcing:
+                forced = ops.routing_frame_or(forced, torch.empty_like(forced), Fr)
+
+        lat = hidden_states.to(dev, bf).contiguous()
+        txt = encoder_hidden_states.to(dev, bf).contiguous()
+        af = af_matrix.to(dev, torch.float32).contiguous() if af_matrix is not None else None
+        out = torch.empty(B, Fr, self.out_cols // (p * p), Hl, Wl, device=dev, dtype=bf)
+
+        x_all = ws.get("x", (B, N, D))
+        xn = ws.get("xn", (N, D))
+        qkv = ws.get("qkv", (N, 3 * D))
+        att = ws.get("att", (N, D))
+        ffh = ws.get("ffh", (N, 4 * D))
+        patches = ws.get("patches", (Nv, self.patch_k))
+        routing = ws.get("routing", (Nv, C), torch.float32)
+        aw = ws.get("aud_w", (Nv, C), torch.float32)
+        awsum = ws.get("aud_wsum", (Nv,), torch.float32)
+
+        for b in range(B):
+            x = x_all[b]
+            xv = x[T:]
+            mod = ada[b]
+            # ---- embed (transformer.py:690-695)
+            ops.gemm(txt[b], self.text_w, x[:T], bias=self.text_b)
+            ops.patchify(lat[b], patches)
+            ops.gemm(patches, self.patch_w, xv, bias=self.patch_b)
+            if tap and b == 0:
+                tap("embed_video", xv)
+            routing.zero_()
+            rt = routing if use_router else forced  # forced masks replace the router output (transformer.py:813-819)
+            ca = 0
+            for i, L in enumerate(self.layers):
+                o = i * 12 * D
+                sh, sc, g, esh, esc, eg = (mod[o + k * D: o + (k + 1) * D] for k in range(6))
+                sh2, sc2, g2, esh2, esc2, eg2 = (mod[o + (6 + k) * D: o + (7 + k) * D] for k in range(6))
+                # ---- DiT block (transformer.py:223-262)
+                ops.layernorm_modulate(x, xn, eps=L["ln1"][2], gamma=L["ln1"][0], beta=L["ln1"][1], mod_a=(esc, esh),
+                                       mod_b=(sc, sh), split_row=T)
+                ops.gemm(xn, L["w_qkv"], qkv, bias=L["b_qkv"], mode=ops.EPI_QKV, split_row=T, qk_cols=2 * D,
+                         ln_eps=L["qk_eps"], rope=(cos, sin), nq=L["nq"], nk=L["nk"])
+                ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, 1, N, self.heads)
+                ops.gemm(att, L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g, split_row=T)
+                ops.layernorm_modulate(x, xn, eps=L["ln2"][2], gamma=L["ln2"][0], beta=L["ln2"][1], mod_a=(esc2, esh2),
+                                       mod_b=(sc2, sh2), split_row=T)
+                ops.gemm(xn, L["w_f1"], ffh, bias=L["b_f1"], act=ops.ACT_GELU_TANH)
+                ops.gemm(ffh, L["w_f2"], x, bias=L["b_f2"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg2, gate_b=g2,
+                         split_row=T)
+                if tap and b == 0:
+                    tap(f"block{i}.video", xv)
+                    tap(f"block{i}.text", x[:T])
+                # ---- face cross-attention + routing (transformer.py:737-833)
+                if m.is_train_face and i % m.cross_attn_interval == 0:
+                    Fc = self.face[ca]
+                    xnv = xn[:Nv]
+                    ops.layernorm_modulate(xv, xnv, eps=Fc["ln"][2], gamma=Fc["ln"][0], beta=Fc["ln"][1])
+                    qf = ws.get("face_q", (Nv, Fc["w_q"].shape[0]))
+                    ops.gemm(xnv, Fc["w_q"], qf)
+                    if use_router:
+                        run_router(self.router, ws, qf, pro["kmat"][b][ca], ca, C, Fr, hw, routing)
+                        if tap and b == 0:
+                            tap(f"ca{ca}.router", routing)
+                    fa = ws.get("face_a", qf.shape)
+                    k = pro["face_k"][b][ca]
+                    ops.xattn_kv32(qf, k, pro["face_vt"][b][ca], rt, fa, k.shape[1], k.shape[3], C, 1,
+                                   k.shape[3] ** -0.5)
+                    ops.gemm(fa, Fc["w_o"], xv, mode=ops.EPI_RESIDUAL, resid=xv, alpha=float(m.local_face_scale))
+                    if tap and b == 0:
+                        tap(f"ca{ca}.video", xv)
+                    ca += 1
+                # ---- audio cross-attention (transformer.py:858-936)
+                if has_audio and i % m.audio_attn_interval == 0:
+                    la = i // m.audio_attn_interval
+                    A = self.audio[la]
+                    ops.audio_weights(af[b], rt, aw, awsum)
+                    xnv = xn[:Nv]
+                    ops.layernorm_modulate(xv, xnv, eps=A["ln"][2], gamma=A["ln"][0], beta=A["ln"][1])
+                    qa = att[:Nv]
+                    ops.gemm(xnv, A["w_q"], qa, bias=A["b_q"])
+                    aa = qkv[:Nv, :D]
+                    k = pro["aud_k"][b][la]
+                    ops.xattn_kv32(qa, k, pro["aud_vt"][b][la], aw, aa, k.shape[1], k.shape[3], C, Fr, k.shape[3] ** -0.5)
+                    ops.gemm(aa, A["w_o"], xv, bias=A["b_o"], mode=ops.EPI_RESIDUAL, resid=xv, row_bias_scale=awsum)
+                    if tap and b == 0:
+                        tap(f"audio{i}.weights", aw)
+                        tap(f"audio{i}.video", xv)
+            # ---- head (transformer.py:938-957)
+            o = self.L * 12 * D
+            shift, scale = ada[b][o: o + D], ada[b][o + D: o + 2 * D]
+            xnv = xn[:Nv]
+            ops.layernorm_modulate(xv, xnv, eps=self.nf[2], gamma=self.nf[0], beta=self.nf[1])
+            ops.layernorm_modulate(xnv, xnv, eps=self.no[2], gamma=self.no[0], beta=self.no[1], mod_b=(scale, shift))
+            y = ws.get("proj", (Nv, self.proj_w.shape[0]))
+            ops.gemm(xnv, self.proj_w, y, bias=self.proj_b)
+            ops.unpatchify(y, out[b])
+        return out

@@ -77,3 +77,150 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.
     check(rc, "attention_d64")
     LAUNCHES += 1
     return out
+
+
+def _f32(t: Optional[torch.Tensor], name: str):
+    if t is not None and (t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous()):
+        raise RuntimeError(f"bya_b200: {name} must be a contiguous CUDA fp32 tensor")
+    return t
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def layernorm_modulate(x, out, *, eps=1e-5, gamma=None, beta=None, mod_a=None, mod_b=None, split_row=0, add=None):
+    """out = (LN(x)*gamma+beta)*(1+scale)+shift (+add[row % add_rows]); mod_* = (scale, shift) fp32 [dim] for rows
+    < split_row (a) and >= split_row (b)."""
+    _bf16_2d(x, "x"), _bf16_2d(out, "out")
+    rows, dim = x.shape
+    sa, ha = (mod_a if mod_a is not None else (None, None))
+    sb, hb = (mod_b if mod_b is not None else (None, None))
+    for t in (sa, ha, sb, hb):
+        _f32(t, "modulation")
+    add_rows = 0
+    if add is not None:
+        _bf16_2d(add, "add")
+        if not add.is_contiguous() or add.shape[1] != dim:
+            raise RuntimeError("bya_b200.layernorm_modulate: add must be contiguous [rows, dim]")
+        add_rows = add.shape[0]
+    rc = lib().bya_layernorm_modulate(_stream(), _ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, dim,
+                                      ctypes.c_float(eps), _ptr(gamma), _ptr(beta), _ptr(sa), _ptr(ha), _ptr(sb),
+                                      _ptr(hb), split_row, _ptr(add), add_rows)
+    check(rc, "layernorm_modulate")
+    _count()
+    return out
+
+
+def gemv(w, bias, x, y, in_act=0, out_act=0):
+    """y[b] = out_act(W @ in_act(x[b]) + bias); W bf16 [N,K], x fp32 [B,K], y fp32 [B,N]."""
+    _bf16_2d(w, "w"), _f32(x, "x"), _f32(y, "y")
+    if not w.is_contiguous():
+        raise RuntimeError("bya_b200.gemv: W must be contiguous")
+    B, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K or tuple(y.shape) != (B, N):
+        raise RuntimeError("bya_b200.gemv: shape mismatch")
+    check(lib().bya_gemv(_stream(), _ptr(w), _ptr(bias), _ptr(x), _ptr(y), B, N, K, in_act, out_act), "gemv")
+    _count()
+    return y
+
+
+def timestep_features(t, out):
+    if t.dtype != torch.int64 or not t.is_cuda:
+        raise RuntimeError("bya_b200.timestep_features: timestep must be CUDA int64")
+    _f32(out, "out")
+    check(lib().bya_timestep_features(_stream(), _ptr(t), _ptr(out), out.shape[0], out.shape[1]), "timestep_features")
+    _count()
+    return out
+
+
+def patchify(latents, out):
+    """latents bf16 [F,C,H,W] contiguous -> out bf16 [F*H/2*W/2, ld] (zero padded columns)."""
+    F, C, H, W = latents.shape
+    if latents.dtype != torch.bfloat16 or not latents.is_contiguous():
+        raise RuntimeError("bya_b200.patchify: latents must be contiguous bf16")
+    _bf16_2d(out, "out")
+    check(lib().bya_patchify(_stream(), _ptr(latents), _ptr(out), F, C, H, W, out.stride(0)), "patchify")
+    _count()
+    return out
+
+
+def unpatchify(y, out):
+    """y bf16 [F*gh*gw, >=C*4] -> out bf16 [F,C,2gh,2gw]."""
+    F, C, H, W = out.shape
+    _bf16_2d(y, "y")
+    if out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise RuntimeError("bya_b200.unpatchify: out must be contiguous bf16")
+    check(lib().bya_unpatchify(_stream(), _ptr(y), y.stride(0), _ptr(out), F, C, H // 2, W // 2), "unpatchify")
+    _count()
+    return out
+
+
+def router_head(x, w, b, r, rows, chars):
+    _bf16_2d(x, "x"), _f32(r, "r")
+    check(lib().bya_router_head(_stream(), _ptr(x), _ptr(w), _ptr(b), _ptr(r), rows, chars, x.shape[1]), "router_head")
+    _count()
+    return r
+
+
+def xattn_kv32(q, K, Vt, w, out, heads, head_dim, chars, kv_frames, scale):
+    """Routed 32-key cross-attention; q/out bf16 [tokens, heads*head_dim] views, K [G,H,32,d], Vt [G,H,d,32]."""
+    _bf16_2d(q, "q"), _bf16_2d(out, "out"), _f32(w, "w")
+    tokens = q.shape[0]
+    G = chars * kv_frames
+    if tuple(K.shape) != (G, heads, 32, head_dim) or tuple(Vt.shape) != (G, heads, head_dim, 32):
+        raise RuntimeError(f"bya_b200.xattn_kv32: K{tuple(K.shape)} / Vt{tuple(Vt.shape)} do not match")
+    if not (K.is_contiguous() and Vt.is_contiguous() and K.dtype == torch.bfloat16 and Vt.dtype == torch.bfloat16):
+        raise RuntimeError("bya_b200.xattn_kv32: K / Vt must be contiguous bf16")
+    if w is not None and tuple(w.shape) != (tokens, chars):
+        raise RuntimeError("bya_b200.xattn_kv32: w must be [tokens, chars]")
+    rc = lib().bya_xattn_kv32(_stream(), _ptr(q), q.stride(0), _ptr(K), _ptr(Vt), _ptr(w), _ptr(out), out.stride(0),
+                              tokens, heads, head_dim, chars, kv_frames, ctypes.c_float(scale))
+    check(rc, "xattn_kv32")
+    _count()
+    return out
+
+
+def small_attention(qkv, out, n_seq, seq_len, heads, inner, outer_stride, tok_stride, scale=0.125):
+    _bf16_2d(qkv, "qkv"), _bf16_2d(out, "out")
+    rc = lib().bya_small_attention(_stream(), _ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), n_seq, seq_len, heads,
+                                   inner, ctypes.c_longlong(outer_stride), ctypes.c_longlong(tok_stride),
+                                   ctypes.c_float(scale))
+    check(rc, "small_attention")
+    _count()
+    return out
+
+
+def masks_to_routing(masks, frames, grid_h, grid_w, index_mask=None, logits=None):
+    """masks uint8 [C,T,H,W] (CUDA) -> (index_mask int64 [Nv], logits fp32 [Nv,C]); bit-exact vs the reference."""
+    if masks.dtype != torch.uint8 or not masks.is_cuda or not masks.is_contiguous() or masks.dim() != 4:
+        raise RuntimeError("bya_b200.masks_to_routing: masks must be contiguous CUDA uint8 [C,T,H,W]")
+    C, T, H, W = masks.shape
+    n = frames * grid_h * grid_w
+    if index_mask is None:
+        index_mask = torch.empty(n, dtype=torch.int64, device=masks.device)
+    if logits is None:
+        logits = torch.empty(n, C, dtype=torch.float32, device=masks.device)
+    rc = lib().bya_masks_to_routing(_stream(), _ptr(masks), C, T, H, W, frames, grid_h, grid_w, _ptr(index_mask),
+                                    _ptr(logits))
+    check(rc, "masks_to_routing")
+    _count()
+    return index_mask, logits
+
+
+def routing_frame_or(logits, out, frames):
+    _f32(logits, "logits"), _f32(out, "out")
+    n, C = logits.shape
+    check(lib().bya_routing_frame_or(_stream(), _ptr(logits), _ptr(out), frames, n // frames, C), "routing_frame_or")
+    _count()
+    return out
+
+
+def audio_weights(af, routing, w, wsum=None):
+    _f32(af, "af"), _f32(routing, "routing"), _f32(w, "w"), _f32(wsum, "wsum")
+    n, C = routing.shape
+    check(lib().bya_audio_weights(_stream(), _ptr(af), _ptr(routing), _ptr(w), _ptr(wsum), n, C), "audio_weights")
+    _count()
+    return w

@@ -71,6 +71,57 @@ int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W, int ldw, 
 int bya_attention_d64(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo,
                       int batch, int seq, int heads, float scale);
 
+/* ---------------------------------------------------------------- routed small-KV cross-attention (32 keys)
+ * out[n, h*d..] = sum_c w[n,c] * softmax_k(scale * q[n,h,:].K[g][h][k][:]) @ V[g][h],  g = c*kv_frames + n/(tokens/kv_frames)
+ * K  : [chars*kv_frames][heads][32][head_dim],  Vt : [chars*kv_frames][heads][head_dim][32]  (V transposed), bf16.
+ * w  : [tokens, chars] fp32 routing / audio weights (NULL -> 1).  head_dim in {64,128}, chars in {1,2,3}.
+ * Replaces the attention core + routed blend of PerceiverCrossAttention (router.py:256-273 with transformer.py:821-822)
+ * and of the audio cross-attention (audio_model.py:253-256 with transformer.py:925-926). */
+int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* K, const void* Vt, const float* w, void* out,
+                   int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames, float scale);
+
+/* Router temporal / multi-ID self-attention (router.py:478-488): n_seq sequences of seq_len (<=32) rows of the
+ * [rows, 3*heads*64] qkv matrix, rows of one sequence `tok_stride` apart, first row (s/inner)*outer_stride + s%inner. */
+int bya_small_attention(void* stream, const void* qkv, int ld, void* out, int ldo, int n_seq, int seq_len, int heads,
+                        int inner, long long outer_stride, long long tok_stride, float scale);
+
+/* ---------------------------------------------------------------- row kernels (HBM-bound)
+ * out = (LN(x)*gamma+beta) * (1+scale[cls]) + shift[cls] (+ add[row % add_rows]); cls a: rows < split_row, b: others.
+ * dim in {512,768,1024,2048,3072}.  gamma/beta/add bf16, scale/shift fp32; any of them may be NULL.
+ * Replaces nn.LayerNorm + CogVideoXLayerNormZero / AdaLayerNorm modulation (transformer.py:233,:251,:944-948) and the
+ * LayerNorms of router.py:247-248,:380-399,:475-491 and audio_model.py:249. */
+int bya_layernorm_modulate(void* stream, const void* x, int ldx, void* out, int ldo, int rows, int dim, float eps,
+                           const void* gamma, const void* beta, const float* scale_a, const float* shift_a,
+                           const float* scale_b, const float* shift_b, int split_row, const void* add, int add_rows);
+
+/* y[b,n] = out_act(bias[n] + sum_k W[n,k] * in_act(x[b,k]));  act: 0 none, 1 SiLU; batch <= 4; fp32 in/out.
+ * One call evaluates every adaLN linear of a step (CogVideoXLayerNormZero.linear x 2L + AdaLayerNorm.linear,
+ * transformer.py:198,212,420) on the shared temb; also time_embedding.linear_1/2 (transformer.py:686). */
+int bya_gemv(void* stream, const void* W, const void* bias, const float* x, float* y, int batch, int N, int K,
+             int in_act, int out_act);
+
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0) (transformer.py:680): out [batch, dim] fp32 */
+int bya_timestep_features(void* stream, const int64_t* t, float* out, int batch, int dim);
+
+/* im2col of CogVideoXPatchEmbed's Conv2d(k=2,s=2) for one batch element: latents [F,C,H,W] -> [F*H/2*W/2, ldo] with
+ * columns (c,dy,dx), zero padded to ldo (transformer.py:690); and the inverse scatter of transformer.py:955-957. */
+int bya_patchify(void* stream, const void* latents, void* out, int frames, int channels, int height, int width, int ldo);
+int bya_unpatchify(void* stream, const void* y, int ldy, void* out, int frames, int channels, int grid_h, int grid_w);
+
+/* r[n,c] = sigmoid(w . x[c*rows+n,:] + b): MultiIPRouter.final_proj + permute (router.py:408-411); r fp32 [rows,chars] */
+int bya_router_head(void* stream, const void* x, const void* w, const void* b, float* r, int rows, int chars, int dim);
+
+/* ---------------------------------------------------------------- 3-D masks -> routing (bit-exact integer/0-1 path)
+ * masks uint8 [chars,T,H,W] (>0 inside) -> index_mask int64 [frames*grid_h*grid_w] (-1 background, later character
+ * wins; may be NULL) and one-hot logits fp32 [tokens, chars].  util/utils.py:871-936 (+ :481-514). */
+int bya_masks_to_routing(void* stream, const uint8_t* masks, int chars, int T, int H, int W, int frames, int grid_h,
+                         int grid_w, int64_t* index_mask, float* logits);
+/* OR (max) over the frame axis broadcast back to all frames: transformer.py:815-818 */
+int bya_routing_frame_or(void* stream, const float* logits, float* out, int frames, int tokens_per_frame, int chars);
+/* w[n,c] = 1 - max_{c'!=c} (af @ r[n])[c'] (== 1 - swap(af@r) for two characters), wsum[n] = sum_c w[n,c] (may be
+ * NULL): transformer.py:860-863,:899-900 */
+int bya_audio_weights(void* stream, const float* af, const float* routing, float* w, float* wsum, int tokens, int chars);
+
 #ifdef __cplusplus
 }
 #endif

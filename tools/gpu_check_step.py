@@ -1,0 +1,81 @@
+"""End-to-end parity of the CUDA step against the restated oracle on the GPU box (bisecting tool; prints per-tap error)."""
+import sys, os, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bya_b200
+from bya_b200 import ops
+from bya_b200.synth import CONFIGS, PathConfig, fill_module, make_inputs
+from bya_b200.transformer import BindyouravatarTransformer3DModel
+from oracle import restated
+
+def cos(a, b):
+    a, b = a.flatten().double(), b.flatten().double()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "c1"
+    forced = "forced" in sys.argv
+    layers = None
+    for a in sys.argv:
+        if a.startswith("L="):
+            layers = int(a[2:])
+    cfg = CONFIGS[name]
+    if layers:
+        import dataclasses
+        cfg = dataclasses.replace(cfg, num_layers=layers)
+    torch.manual_seed(0)
+    t0 = time.time()
+    model = BindyouravatarTransformer3DModel(**cfg.ctor_kwargs()).eval()
+    model.router.set_grid(cfg.frames, cfg.grid_h, cfg.grid_w)
+    fill_module(model, 0)
+    model = model.to("cuda", torch.bfloat16)
+    print("model built", time.time() - t0, flush=True)
+    inp = make_inputs(cfg, 1234, device="cuda", dtype=torch.bfloat16, forced_masks=forced)
+    inp["timestep"] = inp["timestep"].cuda()
+    taps = {}
+    out = model(**inp, taps=taps)[0]
+    torch.cuda.synchronize()
+    print("bya step done; launches", ops.LAUNCHES, "finite", bool(torch.isfinite(out.float()).all()), flush=True)
+    # timing
+    for _ in range(2):
+        model(**inp)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); s.record()
+    n = 3
+    for _ in range(n):
+        model(**inp)
+    e.record(); torch.cuda.synchronize()
+    print(f"bya step time {s.elapsed_time(e)/n:.2f} ms", flush=True)
+
+    sd = {k: v.float() for k, v in model.state_dict().items()}
+    oin = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in inp.items()}
+    oin["id_cond"] = [t.float() for t in inp["id_cond"]]
+    oin["id_vit_hidden"] = [[t.float() for t in l] for l in inp["id_vit_hidden"]]
+    oin["image_rotary_emb"] = inp["image_rotary_emb"]
+    otaps = {}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ref = restated.step(sd, cfg, **oin, taps=otaps)
+    torch.cuda.synchronize()
+    for k in otaps:
+        if k in taps:
+            a, b = taps[k].float().reshape(-1), otaps[k].float().reshape(-1)
+            if a.numel() != b.numel():
+                print(f"{k:24s} SHAPE {tuple(taps[k].shape)} vs {tuple(otaps[k].shape)}")
+                continue
+            print(f"{k:24s} cos={cos(a,b):.6f} max_abs={float((a-b).abs().max()):.4e} ref_absmax={float(b.abs().max()):.3e}")
+    o, r = out.float().cpu(), ref.float().cpu()
+    print(f"OUTPUT cos={cos(o,r):.6f} max_abs={float((o-r).abs().max()):.4e} ref_absmax={float(r.abs().max()):.3e}")
+    # torch-bf16 noise floor
+    sdb = {k: v.bfloat16() for k, v in sd.items()}
+    bin_ = dict(inp)
+    refb = restated.step(sdb, cfg, **bin_).float().cpu()
+    print(f"NOISE FLOOR (torch bf16 vs fp32) cos={cos(refb,r):.6f} max_abs={float((refb-r).abs().max()):.4e}")
+    gp = os.path.join(ROOT, "tests", "golden", "step_c1_soft.pt")
+    if name == "c1" and not forced and not layers and os.path.exists(gp):
+        g = torch.load(gp)
+        print(f"GOLDEN(reference fp32) vs bya: cos={cos(o, g['output'])} max_abs={float((o-g['output']).abs().max()):.4e}")
+        print(f"GOLDEN(reference fp32) vs restated(bf16-rounded weights): cos={cos(r, g['output'])}")
+
+main()
