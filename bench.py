@@ -1,0 +1,382 @@
+"""bench.py — denoising steps/s of the B200-native Bind-Your-Avatar hot path (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W            one process, one B200
+  torchrun --nproc-per-node N ... bench.py --gpus N ...    one rank per GPU (NCCL); sequence-parallel step
+  python bench.py --impl reference ...                     the reference's algorithm on the host CPU cores (oracle port)
+
+A "step" = one forward of the 42-layer denoiser at 49 frames 480x720, 2 characters (BASELINE.json configs[1]), B=1,
+learned soft router, audio + face cross-attention on, timestep-invariant prologue RECOMPUTED every step (nothing is
+cached between timed steps).  Prints ONE JSON line (see the task contract for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoising steps/sec (49f 480x720, 2 chars)"
+UNIT = "steps/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_sample(cfg, threads=None, seed=0):
+    """Times the reference's algorithm (oracle port, fp32 torch on the host cores) on a BOUNDED sample of the c2
+    workload: ONE of the 42 layers at the full 13x30x45 grid — one DiT block, one face cross-attention + router call,
+    one audio cross-attention layer — and extrapolates by the layer counts (42 / 21 / 42).  Returns seconds per full step."""
+    import torch
+
+    import bya_b200  # noqa: F401
+    from bya_b200.synth import fill_parameter
+    from bya_b200.rope import rope_3d_tables
+    from oracle import restated
+
+    if threads:
+        torch.set_num_threads(threads)
+    D, Nv, T, C, Fr = cfg.dim, cfg.n_video, cfg.text_len, cfg.chars, cfg.frames
+    g = torch.Generator().manual_seed(seed)
+
+    sd = {}
+
+    def P(name, *shape):
+        t = torch.empty(*shape)
+        fill_parameter(name, t, seed)
+        sd[name] = t
+
+    b = "transformer_blocks.0"
+    for n in ("norm1", "norm2"):
+        P(f"{b}.{n}.linear.weight", 6 * D, 512), P(f"{b}.{n}.linear.bias", 6 * D)
+        P(f"{b}.{n}.norm.weight", D), P(f"{b}.{n}.norm.bias", D)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        P(f"{b}.attn1.{n}.weight", D, D), P(f"{b}.attn1.{n}.bias", D)
+    for n in ("norm_q", "norm_k"):
+        P(f"{b}.attn1.{n}.weight", 64), P(f"{b}.attn1.{n}.bias", 64)
+    P(f"{b}.ff.net.0.proj.weight", 4 * D, D), P(f"{b}.ff.net.0.proj.bias", 4 * D)
+    P(f"{b}.ff.net.2.weight", D, 4 * D), P(f"{b}.ff.net.2.bias", D)
+    ca = "perceiver_cross_attention.0"
+    P(f"{ca}.norm1.weight", 2048), P(f"{ca}.norm1.bias", 2048), P(f"{ca}.norm2.weight", D), P(f"{ca}.norm2.bias", D)
+    P(f"{ca}.to_q.weight", 2048, D), P(f"{ca}.to_kv.weight", 4096, 2048), P(f"{ca}.to_out.weight", D, 2048)
+    for n, d in (("norm", 512), ("norm_q", 2048), ("norm_k", 2048)):
+        P(f"router.{n}.weight", d), P(f"router.{n}.bias", d)
+    P("router.to_q.0.weight", 2048, 2048), P("router.to_k.0.weight", 2048, 2048)
+    sd["router.pos_emb"] = restated.router_pos_emb(Fr, cfg.grid_w, cfg.grid_h)
+    for i in range(4):
+        s = f"router.spatial_temporal_layers.{i}"
+        for a in ("spatial_attn", "temporal_attn", "multi_id_attn"):
+            for n in ("to_q", "to_k", "to_v", "to_out.0"):
+                P(f"{s}.{a}.{n}.weight", 512, 512), P(f"{s}.{a}.{n}.bias", 512)
+        for n in ("norm1", "norm2", "norm3", "norm4"):
+            P(f"{s}.{n}.weight", 512), P(f"{s}.{n}.bias", 512)
+        for n in ("mlp.0", "mlp.2"):
+            P(f"{s}.{n}.weight", 512, 512), P(f"{s}.{n}.bias", 512)
+    P("router.final_proj.0.weight", 1, 512), P("router.final_proj.0.bias", 1)
+    al = "audio_model.layers.0"
+    P(f"{al}.norm_q.weight", D), P(f"{al}.norm_q.bias", D)
+    P(f"{al}.attn.to_q.weight", D, D), P(f"{al}.attn.to_q.bias", D)
+    P(f"{al}.attn.to_k.weight", D, 768), P(f"{al}.attn.to_k.bias", D)
+    P(f"{al}.attn.to_v.weight", D, 768), P(f"{al}.attn.to_v.bias", D)
+    P(f"{al}.attn.to_out.0.weight", D, D), P(f"{al}.attn.to_out.0.bias", D)
+
+    h = torch.randn(1, Nv, D, generator=g)
+    e = torch.randn(1, T, D, generator=g)
+    temb = torch.randn(1, 512, generator=g) * 0.3
+    rope = rope_3d_tables(64, Fr, cfg.grid_h, cfg.grid_w)
+    face = torch.randn(C, 32, 2048, generator=g)
+    actx = torch.randn(C, Fr, 32, 768, generator=g)
+
+    def run_once():
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            h2, e2 = restated.dit_block(sd, b, h, e, temb, rope, cfg.num_attention_heads)
+            t1 = time.perf_counter()
+            feat, q_out, k_out = restated.face_cross_attention(sd, ca, face, h2)
+            r = restated.router(sd, q_out, k_out, 0, Fr, cfg.grid_h, cfg.grid_w)
+            _ = torch.einsum("nc,cnd->nd", r[0], feat)
+            t2 = time.perf_counter()
+            w = restated.audio_weights(torch.eye(C), r[0])
+            af = restated.audio_layer(sd, 0, actx, h2, Fr)
+            _ = torch.einsum("nc,cnd->nd", w, af)
+            t3 = time.perf_counter()
+        L = cfg.num_layers
+        return (t1 - t0) * L + (t2 - t1) * (L // cfg.cross_attn_interval) + (t3 - t2) * (L // cfg.audio_attn_interval), t3 - t0
+
+    return run_once
+
+
+def run_reference_arm(args):
+    import torch
+
+    import bya_b200  # noqa: F401
+    from bya_b200.synth import CONFIGS
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS["c2"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run_once = cpu_reference_sample(cfg, cores)
+    budget = float(os.environ.get("BYA_REF_BUDGET_S", "240"))
+    t_start = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
+        run_once()
+    ests, done = [], 0
+    for _ in range(max(args.steps, 1)):
+        est, _ = run_once()
+        ests.append(est)
+        done += 1
+        if time.perf_counter() - t_start > budget:
+            break
+    sec = sum(ests) / len(ests)
+    val = 1.0 / sec
+    sample = ("1 of 42 layers at the full 13x30x45 grid per step (one DiT block + one face cross-attention/router call + "
+              "one audio layer; fp32 torch restatement of the reference), extrapolated by layer counts 42/21/42")
+    line = {
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 1),
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": "c2: 42-layer denoiser, 49f 480x720 (latent 13x60x90, 17776 tokens), 2 characters, B=1",
+                   "note": "reference tree absent on the GPU box -> oracle port (oracle/restated.py) on host cores"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def build_model(cfg, device, seed=0):
+    import torch
+
+    from bya_b200.synth import fill_module
+    from bya_b200.transformer import BindyouravatarTransformer3DModel
+
+    with torch.device("meta"):
+        model = BindyouravatarTransformer3DModel(**cfg.ctor_kwargs())
+    model = model.to(torch.bfloat16).to_empty(device=device).eval()
+    model.router.frames, model.router.height, model.router.width = cfg.frames, cfg.grid_w, cfg.grid_h
+    model.router.pos_emb = model.router._create_positional_embedding().to(device, torch.bfloat16)
+    fill_module(model, seed)
+    return model
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="bya", choices=["bya", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--layers", type=int, default=0, help="debug: override the layer count (the result is then NOT the metric)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import bya_b200  # noqa: F401
+    from bya_b200 import ops
+    from bya_b200.synth import CONFIGS, make_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    cfg = CONFIGS[args.config]
+    if args.layers:
+        import dataclasses
+
+        cfg = dataclasses.replace(cfg, num_layers=args.layers)
+
+    # ---- CPU baseline (rank 0, N=1 only; bounded sample) before the GPU is busy
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        run_once = cpu_reference_sample(CONFIGS["c2"], cores)
+        sec, _ = run_once()
+        cpu_base = {"value": 1.0 / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": "1 of 42 layers at the full 13x30x45 grid (DiT block + face cross-attn/router + audio layer), fp32 "
+                              "torch restatement of the reference on the host cores, one run, extrapolated by layer counts 42/21/42"}
+
+    model = build_model(cfg, dev)
+    model.cache_prologue = False  # nothing is cached between timed steps
+    if world > 1:
+        from bya_b200 import sp
+
+        sp.enable(model, dist.group.WORLD)
+    inp = make_inputs(cfg, 1234, device=dev, dtype=torch.bfloat16)
+
+    def one_step():
+        return model(**inp)[0]
+
+    for _ in range(W):
+        one_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.PROFILE = {"self_attention": []}
+    l0 = ops.LAUNCHES
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        one_step()
+    e.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = s.elapsed_time(e) / args.steps
+    launches = (ops.LAUNCHES - l0) // args.steps
+    prof = ops.PROFILE["self_attention"]
+    ops.PROFILE = None
+    fa_ms = sum(a.elapsed_time(b) for a, b in prof) / max(len(prof), 1)
+    if sampler:
+        sampler.stop_flag = True
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- e2e: the public call with HOST (pinned) inputs; H2D of every input + D2H of the prediction inside the timing
+    def pin(x):
+        return x.detach().cpu().pin_memory()
+
+    host = {k: (pin(v) if torch.is_tensor(v) else v) for k, v in inp.items()}
+    host["id_cond"] = [pin(t_) for t_ in inp["id_cond"]]
+    host["id_vit_hidden"] = [[pin(t_) for t_ in l] for l in inp["id_vit_hidden"]]
+    host["image_rotary_emb"] = tuple(pin(t_) for t_ in inp["image_rotary_emb"])
+
+    def nbytes(v):
+        if torch.is_tensor(v):
+            return v.numel() * v.element_size()
+        return sum(nbytes(x) for x in v)
+
+    h2d = sum(nbytes(v) for v in host.values())
+    out_host = torch.empty(one_step().shape, dtype=torch.bfloat16).pin_memory()
+
+    def to_dev(v):
+        if torch.is_tensor(v):
+            return v.to(dev, non_blocking=True)
+        return type(v)(to_dev(x) for x in v)
+
+    def e2e_step():
+        d = {k: to_dev(v) for k, v in host.items()}
+        out_host.copy_(model(**d)[0], non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e.record()
+    torch.cuda.synchronize()
+    ms_e2e = s.elapsed_time(e) / args.steps
+    t = torch.tensor([ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+
+    if rank == 0:
+        peaks, src = measured_peaks()
+        N = cfg.n_tokens
+        heads_local = cfg.num_attention_heads // world
+        fa_flops = 4.0 * N * N * 64 * heads_local * cfg.batch  # algorithmic FLOPs of one self-attention launch
+        achieved = fa_flops / (fa_ms * 1e-3) / 1e12 if fa_ms > 0 else None
+        peak = peaks["bf16_tflops_sustained"]
+        line = {
+            "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: {cfg.num_layers}-layer denoiser, 49f 480x720 (latent {cfg.frames}x60x90 -> "
+                                   f"{cfg.n_tokens} tokens), {cfg.chars} characters, B={cfg.batch}, soft router, face+audio "
+                                   "cross-attention, prologue recomputed every step",
+                       "parallelism": "single GPU" if world == 1 else f"ulysses sp{world}",
+                       "l2": "working set (17 GB of weights + >1 GB activations per step) exceeds the 126 MB L2; no flush needed",
+                       "weights": "random-init, seeded (bya_b200.synth)"},
+            "clocks": sampler.summary() if sampler else None,
+            "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": nbytes(out_host)},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "fa_fwd_kernel (joint self-attention)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "launch_ms": fa_ms,
+                         "step_tflops": _step_tflops(cfg) / (ms * 1e-3) / world, "step_frac_of_peak": _step_tflops(cfg) / (ms * 1e-3) / world / peak},
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _step_tflops(cfg):
+    """De-duplicated algorithmic TFLOP of one step."""
+    N, Nv, D, C, Fr, L = cfg.n_tokens, cfg.n_video, cfg.dim, cfg.chars, cfg.frames, cfg.num_layers
+    hw = Nv // Fr
+    dit = 8 * N * D * D + 4 * N * N * D + 16 * N * D * D
+    face = 2 * Nv * D * 2048 * 2 + C * 4 * Nv * 32 * 2048
+    router = 2 * Nv * 2048 * 2048 + C * 2 * Nv * 2048 * 512 / 16 + 4 * (C * Nv * 14 * 2 * 512 * 512 + C * Fr * 4 * hw * hw * 512)
+    audio = 2 * 2 * Nv * D * D + C * 4 * Nv * 32 * D
+    total = L * dit + (L // cfg.cross_attn_interval) * (face + router) + (L // cfg.audio_attn_interval) * audio
+    return cfg.batch * total / 1e12
+
+
+if __name__ == "__main__":
+    main()

@@ -350,7 +350,7 @@ class StepEngine:
                                        mod_b=(sc, sh), split_row=T)
                 ops.gemm(xn, L["w_qkv"], qkv, bias=L["b_qkv"], mode=ops.EPI_QKV, split_row=T, qk_cols=2 * D,
                          ln_eps=L["qk_eps"], rope=(cos, sin), nq=L["nq"], nk=L["nk"])
-                ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, 1, N, self.heads)
+                ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, 1, N, self.heads, tag="self_attention")
                 ops.gemm(att, L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g, split_row=T)
                 ops.layernorm_modulate(x, xn, eps=L["ln2"][2], gamma=L["ln2"][0], beta=L["ln2"][1], mod_a=(esc2, esh2),
                                        mod_b=(sc2, sh2), split_row=T)

@@ -14,6 +14,19 @@ ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
+# Optional live kernel timing (bench.py roofline): PROFILE = {"tag": [(start_event, end_event), ...]}.  Events are
+# recorded on the launching (current) stream, immediately around the launch.
+PROFILE = None
+
+
+def _prof(tag):
+    if PROFILE is None or tag is None or tag not in PROFILE:
+        return None
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    PROFILE[tag].append((s, e))
+    return e
+
 
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
@@ -63,7 +76,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
 
 
 def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, batch: int, seq: int,
-                  heads: int, scale: float = 0.125) -> torch.Tensor:
+                  heads: int, scale: float = 0.125, tag=None) -> torch.Tensor:
     """q/k/v/out: [batch*seq, heads*64] column-slice views (shared row stride for q,k,v) of bf16 matrices."""
     global LAUNCHES
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
@@ -72,8 +85,11 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.
             raise RuntimeError(f"bya_b200.attention_d64: {n} has shape {tuple(t.shape)}")
     if not (q.stride(0) == k.stride(0) == v.stride(0)):
         raise RuntimeError("bya_b200.attention_d64: q, k, v must share a row stride")
+    ev = _prof(tag)
     rc = lib().bya_attention_d64(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
                                  batch, seq, heads, ctypes.c_float(scale))
+    if ev is not None:
+        ev.record()
     check(rc, "attention_d64")
     LAUNCHES += 1
     return out
