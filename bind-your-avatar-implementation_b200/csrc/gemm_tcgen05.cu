@@ -98,7 +98,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, mb * BM, kEvictNormal);
+          if (p.a_kblock) {
+            const int k0 = kb * BK;
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], k0 % p.a_kblock, mb * BM, k0 / p.a_kblock, kEvictNormal);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, mb * BM, kEvictNormal);
+          }
           tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, nb * BN, kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -149,12 +154,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + as * BN + (uint32_t(q * 32) << 16);
       const int col0 = nb * BN;
+      // output column -> element offset within a row (column-block scatter for the sequence-parallel send buffer)
+      auto out_col = [&](int col) -> size_t {
+        return p.col_block ? size_t(col / p.col_block) * size_t(p.col_block_stride) + size_t(col % p.col_block)
+                           : size_t(col);
+      };
 
       if (p.mode == GEMM_EPI_QKV) {
         // one 64-wide head per iteration: + bias, LayerNorm(64) on q/k heads, RoPE on video rows
         const bool is_video = row >= p.split_row;
-        const float* cs = p.rope_cos + size_t(max(row - p.split_row, 0)) * 64;
-        const float* sn = p.rope_sin + size_t(max(row - p.split_row, 0)) * 64;
+        const float* cs = p.rope_cos + size_t(max(row - p.split_row, 0) + p.rope_row0) * 64;
+        const float* sn = p.rope_sin + size_t(max(row - p.split_row, 0) + p.rope_row0) * 64;
+        const int blk = p.qkv_block ? p.qkv_block : p.N;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 64) {
           uint32_t r[64];
@@ -174,8 +185,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             v[i] = __uint_as_float(r[i]) + b0;
             v[i + 1] = __uint_as_float(r[i + 1]) + b1;
           }
-          if (col < p.qk_cols) {
-            const bool is_k = col >= (p.qk_cols >> 1);
+          const int cin = col % blk;  // position inside the [q|k|v] group
+          if (3 * cin < 2 * blk) {
+            const bool is_k = 3 * cin >= blk;
             const __nv_bfloat16* gw = is_k ? p.nk_w : p.nq_w;
             const __nv_bfloat16* gb = is_k ? p.nk_b : p.nq_b;
             float mean = 0.f;
@@ -207,7 +219,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldc + col);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldc + out_col(col));
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               uint4 o;
@@ -274,7 +286,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
-          uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldc + col);
+          uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldc + out_col(col));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 o;
@@ -303,7 +315,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 template <int BN>
 static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
   CUtensorMap ta, tb;
-  int rc = bya_host::encode_tmap_bf16(&ta, A, a.K, a.M, uint64_t(lda) * 2, BK, BM);
+  int rc = a.a_kblock ? bya_host::encode_tmap_bf16(&ta, A, a.a_kblock, a.M, uint64_t(lda) * 2, BK, BM, a.K / a.a_kblock,
+                                                   uint64_t(a.a_kblock_stride) * 2)
+                      : bya_host::encode_tmap_bf16(&ta, A, a.K, a.M, uint64_t(lda) * 2, BK, BM);
   if (rc) return rc;
   rc = bya_host::encode_tmap_bf16(&tb, W, a.K, a.N, uint64_t(ldw) * 2, BK, BN);
   if (rc) return rc;
@@ -332,9 +346,14 @@ extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W
     return BYA_ERR_ALIGN;
   if (a.group_m <= 0) a.group_m = 16;
   if (a.mode == GEMM_EPI_QKV) {
-    if (a.N % 64 || a.qk_cols % 128 || !a.rope_cos || !a.rope_sin || !a.nq_w || !a.nq_b || !a.nk_w || !a.nk_b)
+    const int blk = a.qkv_block ? a.qkv_block : a.N;
+    if (a.N % 64 || blk % 192 || a.N % blk || !a.rope_cos || !a.rope_sin || !a.nq_w || !a.nq_b || !a.nk_w || !a.nk_b)
       return BYA_ERR_SHAPE;
   }
+  if (a.col_block && (a.col_block % 64 || a.N % a.col_block || a.col_block_stride % 8 || a.mode == GEMM_EPI_RESIDUAL))
+    return BYA_ERR_SHAPE;
+  if (a.a_kblock == a.K) a.a_kblock = 0;
+  if (a.a_kblock && (a.a_kblock % BK || a.K % a.a_kblock || a.a_kblock_stride % 8)) return BYA_ERR_SHAPE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a.N % 256 == 0) return launch_gemm<256>(a, A, lda, W, ldw, s);
   if (a.N % 128 == 0) return launch_gemm<128>(a, A, lda, W, ldw, s);

@@ -30,7 +30,8 @@ template <int D, int C>
 __global__ void __launch_bounds__(XA_WARPS * 32)
 xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ K,
                   const __nv_bfloat16* __restrict__ Vt, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                  int ldo, int heads, int tokens_per_frame, int kv_frames, float scale_log2) {
+                  int ldo, int heads, int tokens_per_frame, int kv_frames, float scale_log2, long long tok_begin,
+                  long long tok_count) {
   constexpr int KP = D + 8;    // padded row of the K tile (bank-conflict-free fragment loads)
   constexpr int VP = 32 + 8;   // padded row of the V^T tile
   extern __shared__ __align__(16) uint8_t xa_smem[];
@@ -44,8 +45,14 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
   const int frame = blockIdx.y;
   const int tok0 = blockIdx.x * XA_TOK + warp * 16;               // within the frame
   const int r0 = tok0 + g, r1 = tok0 + g + 8;                     // this thread's two rows (within the frame)
-  const bool ok0 = r0 < tokens_per_frame, ok1 = r1 < tokens_per_frame;
-  const size_t n0 = size_t(frame) * tokens_per_frame + r0, n1 = size_t(frame) * tokens_per_frame + r1;
+  // global token index -> local row of q / w / out (this rank owns tokens [tok_begin, tok_begin + tok_count))
+  const long long blk_lo = (long long)frame * tokens_per_frame + blockIdx.x * XA_TOK;
+  if (blk_lo >= tok_begin + tok_count || blk_lo + XA_TOK <= tok_begin) return;  // no owned token in this block
+  const long long gl0 = (long long)frame * tokens_per_frame + r0 - tok_begin;
+  const long long gl1 = (long long)frame * tokens_per_frame + r1 - tok_begin;
+  const bool ok0 = r0 < tokens_per_frame && gl0 >= 0 && gl0 < tok_count;
+  const bool ok1 = r1 < tokens_per_frame && gl1 >= 0 && gl1 < tok_count;
+  const size_t n0 = size_t(ok0 ? gl0 : 0), n1 = size_t(ok1 ? gl1 : 0);
 
   float wt0[C], wt1[C];
 #pragma unroll
@@ -160,55 +167,75 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
 // Router temporal (L = frames) and multi-ID (L = characters) self-attention, 8 heads x 64 (router.py:478-488).
 // A "sequence" is L rows of the [rows, 3*HD] qkv matrix spaced `tok_stride` rows apart, starting at
 //   base(s) = (s / inner) * outer_stride + (s % inner).
-// One warp per (sequence, head); lanes hold 2 of the 64 head dims; L <= 32.
-template <int MAXL>
-__global__ void __launch_bounds__(256)
+// One THREAD per (query row, head): the 64-wide q, the running output and the online-softmax state live in
+// registers; K/V rows are streamed with 16-byte loads (the L rows of a sequence are shared by its L query threads
+// through L1).  Adjacent threads are adjacent heads of the same row, so every warp load is 4 rows x 1 KB contiguous.
+__global__ void __launch_bounds__(128)
 small_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, __nv_bfloat16* __restrict__ out, int ldo,
                        int n_seq, int L, int heads, int inner, long long outer_stride, long long tok_stride,
-                       float scale) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= n_seq * heads) return;
-  const int s = warp / heads, h = warp % heads;
+                       float scale_log2) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_seq * L * heads;
+  if (tid >= total) return;
+  const int h = int(tid % heads);
+  const long long si = tid / heads;
+  const int s = int(si % n_seq), i = int(si / n_seq);
   const long long base = (long long)(s / inner) * outer_stride + (s % inner);
   const int HD = heads * 64;
-  float2 kx[MAXL], vx[MAXL];
+  float q[64], acc[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + size_t(base + i * tok_stride) * ld + h * 64);
 #pragma unroll
-  for (int j = 0; j < MAXL; ++j) {
-    if (j < L) {
-      const __nv_bfloat16* row = qkv + size_t(base + j * tok_stride) * ld + h * 64 + 2 * lane;
-      const uint32_t ku = *reinterpret_cast<const uint32_t*>(row + HD);
-      const uint32_t vu = *reinterpret_cast<const uint32_t*>(row + 2 * HD);
-      kx[j] = make_float2(bf16_lo(ku), bf16_hi(ku));
-      vx[j] = make_float2(bf16_lo(vu), bf16_hi(vu));
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = qp[c];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        q[c * 8 + 2 * e] = bf16_lo(w[e]) * scale_log2;
+        q[c * 8 + 2 * e + 1] = bf16_hi(w[e]) * scale_log2;
+      }
     }
   }
-  for (int i = 0; i < L; ++i) {
-    const __nv_bfloat16* row = qkv + size_t(base + i * tok_stride) * ld + h * 64 + 2 * lane;
-    const uint32_t qu = *reinterpret_cast<const uint32_t*>(row);
-    const float q0 = bf16_lo(qu) * scale, q1 = bf16_hi(qu) * scale;
-    float sc[MAXL];
-    float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < MAXL; ++j) {
-      if (j < L) {
-        sc[j] = warp_sum(q0 * kx[j].x + q1 * kx[j].y);
-        mx = fmaxf(mx, sc[j]);
+  for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int j = 0; j < L; ++j) {
+    const __nv_bfloat16* row = qkv + size_t(base + j * tok_stride) * ld + h * 64;
+    const uint4* kp = reinterpret_cast<const uint4*>(row + HD);
+    float sc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = kp[c];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc += q[c * 8 + 2 * e] * bf16_lo(w[e]) + q[c * 8 + 2 * e + 1] * bf16_hi(w[e]);
+    }
+    const float mn = fmaxf(m, sc);
+    const float a = exp2f(m - mn), pj = exp2f(sc - mn);
+    m = mn;
+    l = l * a + pj;
+    const uint4* vp = reinterpret_cast<const uint4*>(row + 2 * HD);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = vp[c];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[c * 8 + 2 * e] = acc[c * 8 + 2 * e] * a + pj * bf16_lo(w[e]);
+        acc[c * 8 + 2 * e + 1] = acc[c * 8 + 2 * e + 1] * a + pj * bf16_hi(w[e]);
       }
     }
-    float den = 0.f, a0 = 0.f, a1 = 0.f;
+  }
+  const float inv = 1.f / l;
+  uint4* op = reinterpret_cast<uint4*>(out + size_t(base + i * tok_stride) * ldo + h * 64);
 #pragma unroll
-    for (int j = 0; j < MAXL; ++j) {
-      if (j < L) {
-        const float pj = __expf(sc[j] - mx);
-        den += pj;
-        a0 += pj * vx[j].x;
-        a1 += pj * vx[j].y;
-      }
-    }
-    const float inv = 1.f / den;
-    *reinterpret_cast<uint32_t*>(out + size_t(base + i * tok_stride) * ldo + h * 64 + 2 * lane) =
-        pack_bf16x2(a0 * inv, a1 * inv);
+  for (int c = 0; c < 8; ++c) {
+    uint4 o;
+    o.x = pack_bf16x2(acc[c * 8] * inv, acc[c * 8 + 1] * inv);
+    o.y = pack_bf16x2(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
+    o.z = pack_bf16x2(acc[c * 8 + 4] * inv, acc[c * 8 + 5] * inv);
+    o.w = pack_bf16x2(acc[c * 8 + 6] * inv, acc[c * 8 + 7] * inv);
+    op[c] = o;
   }
 }
 
@@ -218,10 +245,13 @@ using namespace bya;
 
 extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* K, const void* Vt, const float* w,
                               void* out, int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames,
-                              float scale) {
-  if (!q || !K || !Vt || !out || tokens <= 0 || heads <= 0 || kv_frames <= 0 || tokens % kv_frames) return BYA_ERR_SHAPE;
+                              float scale, long long tok_begin, long long total_tokens) {
+  if (total_tokens <= 0) { total_tokens = tokens; tok_begin = 0; }
+  if (!q || !K || !Vt || !out || tokens <= 0 || heads <= 0 || kv_frames <= 0 || total_tokens % kv_frames ||
+      tok_begin < 0 || tok_begin + tokens > total_tokens)
+    return BYA_ERR_SHAPE;
   if (ldq % 2 || ldo % 2) return BYA_ERR_ALIGN;
-  const int tpf = tokens / kv_frames;
+  const int tpf = int(total_tokens / kv_frames);
   dim3 grid((tpf + XA_TOK - 1) / XA_TOK, kv_frames);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const float sl2 = scale * 1.4426950408889634f;
@@ -237,7 +267,7 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
     }                                                                                                             \
     xattn_kv32_kernel<D_, C_><<<grid, XA_WARPS * 32, smem, s>>>(                                                  \
         (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)K, (const __nv_bfloat16*)Vt, w, (__nv_bfloat16*)out,  \
-        ldo, heads, tpf, kv_frames, sl2);                                                                         \
+        ldo, heads, tpf, kv_frames, sl2, tok_begin, tokens);                                                      \
   } while (0)
   if (head_dim == 64 && chars == 1) BYA_XA(64, 1);
   else if (head_dim == 64 && chars == 2) BYA_XA(64, 2);
@@ -252,19 +282,12 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
 
 extern "C" int bya_small_attention(void* stream, const void* qkv, int ld, void* out, int ldo, int n_seq, int seq_len,
                                    int heads, int inner, long long outer_stride, long long tok_stride, float scale) {
-  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || seq_len > 32 || heads <= 0 || inner <= 0) return BYA_ERR_SHAPE;
-  if (ld % 2 || ldo % 2) return BYA_ERR_ALIGN;
-  const long long warps = (long long)n_seq * heads;
-  const int blocks = int((warps + 7) / 8);
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (seq_len <= 4)
-    small_attention_kernel<4><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq, seq_len,
-                                                     heads, inner, outer_stride, tok_stride, scale);
-  else if (seq_len <= 16)
-    small_attention_kernel<16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq,
-                                                      seq_len, heads, inner, outer_stride, tok_stride, scale);
-  else
-    small_attention_kernel<32><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq,
-                                                      seq_len, heads, inner, outer_stride, tok_stride, scale);
+  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0 || inner <= 0) return BYA_ERR_SHAPE;
+  if (ld % 8 || ldo % 8) return BYA_ERR_ALIGN;
+  const long long threads = (long long)n_seq * seq_len * heads;
+  const int blocks = int((threads + 127) / 128);
+  small_attention_kernel<<<blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq, seq_len, heads, inner, outer_stride, tok_stride,
+      scale * 1.4426950408889634f);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }

@@ -253,6 +253,25 @@ class StepEngine:
                 out["aud_vt"].append(vs)
         return out
 
+    # ------------------------------------------------------------------------------------------------ sequence parallel
+    def enable_sequence_parallel(self, group):
+        """Ulysses-style sharding of the [text; video] token axis over `group`: every rank keeps
+        N/P rows and all weights; around the joint self-attention the fused QKV GEMM writes the all-to-all send buffer
+        directly ([dest][rows][q|k|v heads of dest]) and the out-projection reads the returned buffer as a K-blocked A
+        operand, so the two exchanges per layer need no pack / unpack kernels."""
+        import torch.distributed as dist
+
+        self.sp_group = group
+        self.sp_rank = dist.get_rank(group)
+        self.sp_size = P = dist.get_world_size(group)
+        if self.heads % P:
+            raise RuntimeError(f"bya_b200: {self.heads} heads are not divisible by the sequence-parallel size {P}")
+        from .sp import qkv_rows_by_destination
+
+        for L_ in self.layers:
+            L_["w_qkv_sp"] = qkv_rows_by_destination(L_["w_qkv"], self.D, P)
+            L_["b_qkv_sp"] = qkv_rows_by_destination(L_["b_qkv"], self.D, P)
+
     # ------------------------------------------------------------------------------------------------ one step
     @torch.no_grad()
     def step(self, hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,
@@ -271,6 +290,21 @@ class StepEngine:
         use_router = routing_logits_forcing is None
         has_audio = audio_embeds is not None and len(self.audio) > 0
         tap = (lambda k, v: taps.__setitem__(k, v.detach().float().cpu().clone())) if taps is not None else None
+        # ---- this rank's slice of the [text; video] token axis
+        P, rank = getattr(self, "sp_size", 1), getattr(self, "sp_rank", 0)
+        if P > 1:
+            import torch.distributed as dist
+
+            if N % P:
+                raise RuntimeError(f"bya_b200: {N} tokens are not divisible by the sequence-parallel size {P}")
+            if taps is not None:
+                raise RuntimeError("bya_b200: taps are a single-GPU debugging aid")
+        R = N // P                       # local rows
+        n0 = rank * R                    # first local row (global index)
+        Tl = min(max(T - n0, 0), R)      # local text rows
+        Vl = R - Tl                      # local video rows
+        v0 = max(n0 - T, 0)              # global index of the first local video token
+        Dl, Hl_ = D // P, self.heads // P
         if m.is_train_face:
             m.router.set_grid(Fr, gh, gw)
             if self.router.pos.shape[0] != Nv:
@@ -318,24 +352,32 @@ class StepEngine:
         af = af_matrix.to(dev, torch.float32).contiguous() if af_matrix is not None else None
         out = torch.empty(B, Fr, self.out_cols // (p * p), Hl, Wl, device=dev, dtype=bf)
 
-        x_all = ws.get("x", (B, N, D))
-        xn = ws.get("xn", (N, D))
-        qkv = ws.get("qkv", (N, 3 * D))
-        att = ws.get("att", (N, D))
-        ffh = ws.get("ffh", (N, 4 * D))
+        x_all = ws.get("x", (B, R, D))
+        xn = ws.get("xn", (R, D))
+        att = ws.get("att", (R, D))
+        ffh = ws.get("ffh", (R, 4 * D))
         patches = ws.get("patches", (Nv, self.patch_k))
         routing = ws.get("routing", (Nv, C), torch.float32)
-        aw = ws.get("aud_w", (Nv, C), torch.float32)
-        awsum = ws.get("aud_wsum", (Nv,), torch.float32)
+        aw = ws.get("aud_w", (max(Vl, 1), C), torch.float32)
+        awsum = ws.get("aud_wsum", (max(Vl, 1),), torch.float32)
+        if P == 1:
+            qkv = ws.get("qkv", (N, 3 * D))
+        else:
+            qkv_send = ws.get("qkv_send", (P, R, 3 * Dl))   # [dest][local row][q|k|v heads of dest]
+            qkv = ws.get("qkv", (N, 3 * Dl))                # after the exchange: every row, this rank's heads
+            o_send = ws.get("o_send", (N, Dl))              # attention output of this rank's heads, every row
+            o_recv = ws.get("o_recv", (P, R, Dl))           # after the exchange: local rows, [src heads]
 
         for b in range(B):
             x = x_all[b]
-            xv = x[T:]
+            xv = x[Tl:]
             mod = ada[b]
             # ---- embed (transformer.py:690-695)
-            ops.gemm(txt[b], self.text_w, x[:T], bias=self.text_b)
+            if Tl:
+                ops.gemm(txt[b][n0:n0 + Tl], self.text_w, x[:Tl], bias=self.text_b)
             ops.patchify(lat[b], patches)
-            ops.gemm(patches, self.patch_w, xv, bias=self.patch_b)
+            if Vl:
+                ops.gemm(patches[v0:v0 + Vl], self.patch_w, xv, bias=self.patch_b)
             if tap and b == 0:
                 tap("embed_video", xv)
             routing.zero_()
@@ -347,50 +389,71 @@ class StepEngine:
                 sh2, sc2, g2, esh2, esc2, eg2 = (mod[o + (6 + k) * D: o + (7 + k) * D] for k in range(6))
                 # ---- DiT block (transformer.py:223-262)
                 ops.layernorm_modulate(x, xn, eps=L["ln1"][2], gamma=L["ln1"][0], beta=L["ln1"][1], mod_a=(esc, esh),
-                                       mod_b=(sc, sh), split_row=T)
-                ops.gemm(xn, L["w_qkv"], qkv, bias=L["b_qkv"], mode=ops.EPI_QKV, split_row=T, qk_cols=2 * D,
-                         ln_eps=L["qk_eps"], rope=(cos, sin), nq=L["nq"], nk=L["nk"])
-                ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, 1, N, self.heads, tag="self_attention")
-                ops.gemm(att, L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g, split_row=T)
+                                       mod_b=(sc, sh), split_row=Tl)
+                if P == 1:
+                    ops.gemm(xn, L["w_qkv"], qkv, bias=L["b_qkv"], mode=ops.EPI_QKV, split_row=Tl, ln_eps=L["qk_eps"],
+                             rope=(cos, sin), nq=L["nq"], nk=L["nk"])
+                    ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, 1, N, self.heads, tag="self_attention")
+                    ops.gemm(att, L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g, split_row=Tl)
+                else:
+                    ops.gemm(xn, L["w_qkv_sp"], qkv_send[0], bias=L["b_qkv_sp"], mode=ops.EPI_QKV, split_row=Tl,
+                             ln_eps=L["qk_eps"], rope=(cos, sin), rope_row0=v0, nq=L["nq"], nk=L["nk"], qkv_block=3 * Dl,
+                             col_block=3 * Dl, col_block_stride=R * 3 * Dl)
+                    dist.all_to_all_single(qkv.view(P, R, 3 * Dl), qkv_send, group=self.sp_group)
+                    ops.attention_d64(qkv[:, :Dl], qkv[:, Dl:2 * Dl], qkv[:, 2 * Dl:], o_send, 1, N, Hl_, tag="self_attention")
+                    dist.all_to_all_single(o_recv, o_send.view(P, R, Dl), group=self.sp_group)
+                    ops.gemm(o_recv[0], L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g,
+                             split_row=Tl, a_kblock=Dl, a_kblock_stride=R * Dl)
                 ops.layernorm_modulate(x, xn, eps=L["ln2"][2], gamma=L["ln2"][0], beta=L["ln2"][1], mod_a=(esc2, esh2),
-                                       mod_b=(sc2, sh2), split_row=T)
+                                       mod_b=(sc2, sh2), split_row=Tl)
                 ops.gemm(xn, L["w_f1"], ffh, bias=L["b_f1"], act=ops.ACT_GELU_TANH)
                 ops.gemm(ffh, L["w_f2"], x, bias=L["b_f2"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg2, gate_b=g2,
-                         split_row=T)
+                         split_row=Tl)
                 if tap and b == 0:
                     tap(f"block{i}.video", xv)
                     tap(f"block{i}.text", x[:T])
                 # ---- face cross-attention + routing (transformer.py:737-833)
                 if m.is_train_face and i % m.cross_attn_interval == 0:
                     Fc = self.face[ca]
-                    xnv = xn[:Nv]
-                    ops.layernorm_modulate(xv, xnv, eps=Fc["ln"][2], gamma=Fc["ln"][0], beta=Fc["ln"][1])
-                    qf = ws.get("face_q", (Nv, Fc["w_q"].shape[0]))
-                    ops.gemm(xnv, Fc["w_q"], qf)
+                    dq = Fc["w_q"].shape[0]
+                    qpad = ws.get("face_q", (R, dq))         # rows [Tl:] hold the local video queries
+                    qf = qpad[Tl:]
+                    if Vl:
+                        xnv = xn[:Vl]
+                        ops.layernorm_modulate(xv, xnv, eps=Fc["ln"][2], gamma=Fc["ln"][0], beta=Fc["ln"][1])
+                        ops.gemm(xnv, Fc["w_q"], qf)
                     if use_router:
-                        run_router(self.router, ws, qf, pro["kmat"][b][ca], ca, C, Fr, hw, routing)
+                        if P == 1:
+                            q_all = qf
+                        else:  # the router needs whole frames: gather every rank's queries (router runs replicated)
+                            qg = ws.get("face_q_all", (N, dq))
+                            dist.all_gather_into_tensor(qg, qpad, group=self.sp_group)
+                            q_all = qg[T:]
+                        run_router(self.router, ws, q_all, pro["kmat"][b][ca], ca, C, Fr, hw, routing)
                         if tap and b == 0:
                             tap(f"ca{ca}.router", routing)
-                    fa = ws.get("face_a", qf.shape)
-                    k = pro["face_k"][b][ca]
-                    ops.xattn_kv32(qf, k, pro["face_vt"][b][ca], rt, fa, k.shape[1], k.shape[3], C, 1,
-                                   k.shape[3] ** -0.5)
-                    ops.gemm(fa, Fc["w_o"], xv, mode=ops.EPI_RESIDUAL, resid=xv, alpha=float(m.local_face_scale))
+                    if Vl:
+                        fa = ws.get("face_a", (Vl, dq))
+                        k = pro["face_k"][b][ca]
+                        ops.xattn_kv32(qf, k, pro["face_vt"][b][ca], rt[v0:v0 + Vl], fa, k.shape[1], k.shape[3], C, 1,
+                                       k.shape[3] ** -0.5)
+                        ops.gemm(fa, Fc["w_o"], xv, mode=ops.EPI_RESIDUAL, resid=xv, alpha=float(m.local_face_scale))
                     if tap and b == 0:
                         tap(f"ca{ca}.video", xv)
                     ca += 1
                 # ---- audio cross-attention (transformer.py:858-936)
-                if has_audio and i % m.audio_attn_interval == 0:
+                if has_audio and i % m.audio_attn_interval == 0 and Vl:
                     la = i // m.audio_attn_interval
                     A = self.audio[la]
-                    ops.audio_weights(af[b], rt, aw, awsum)
-                    xnv = xn[:Nv]
+                    ops.audio_weights(af[b], rt[v0:v0 + Vl], aw, awsum)
+                    xnv = xn[:Vl]
                     ops.layernorm_modulate(xv, xnv, eps=A["ln"][2], gamma=A["ln"][0], beta=A["ln"][1])
-                    qa = att[:Nv]
+                    qa = att[:Vl]
                     ops.gemm(xnv, A["w_q"], qa, bias=A["b_q"])
-                    aa = qkv[:Nv, :D]
+                    aa = ffh[:Vl, :D]
                     k = pro["aud_k"][b][la]
-                    ops.xattn_kv32(qa, k, pro["aud_vt"][b][la], aw, aa, k.shape[1], k.shape[3], C, Fr, k.shape[3] ** -0.5)
+                    ops.xattn_kv32(qa, k, pro["aud_vt"][b][la], aw, aa, k.shape[1], k.shape[3], C, Fr, k.shape[3] ** -0.5,
+                                   tok_begin=v0, total_tokens=Nv)
                     ops.gemm(aa, A["w_o"], xv, bias=A["b_o"], mode=ops.EPI_RESIDUAL, resid=xv, row_bias_scale=awsum)
                     if tap and b == 0:
                         tap(f"audio{i}.weights", aw)
@@ -398,10 +461,17 @@ class StepEngine:
             # ---- head (transformer.py:938-957)
             o = self.L * 12 * D
             shift, scale = ada[b][o: o + D], ada[b][o + D: o + 2 * D]
-            xnv = xn[:Nv]
-            ops.layernorm_modulate(xv, xnv, eps=self.nf[2], gamma=self.nf[0], beta=self.nf[1])
-            ops.layernorm_modulate(xnv, xnv, eps=self.no[2], gamma=self.no[0], beta=self.no[1], mod_b=(scale, shift))
-            y = ws.get("proj", (Nv, self.proj_w.shape[0]))
-            ops.gemm(xnv, self.proj_w, y, bias=self.proj_b)
+            ypad = ws.get("proj", (R, self.proj_w.shape[0]))
+            if Vl:
+                xnv = xn[:Vl]
+                ops.layernorm_modulate(xv, xnv, eps=self.nf[2], gamma=self.nf[0], beta=self.nf[1])
+                ops.layernorm_modulate(xnv, xnv, eps=self.no[2], gamma=self.no[0], beta=self.no[1], mod_b=(scale, shift))
+                ops.gemm(xnv, self.proj_w, ypad[Tl:], bias=self.proj_b)
+            if P == 1:
+                y = ypad[Tl:]
+            else:
+                yg = ws.get("proj_all", (N, self.proj_w.shape[0]))
+                dist.all_gather_into_tensor(yg, ypad, group=self.sp_group)
+                y = yg[T:]
             ops.unpatchify(y, out[b])
         return out

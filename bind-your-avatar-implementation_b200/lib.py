@@ -18,9 +18,11 @@ class ByaGemmArgs(ctypes.Structure):
         ("resid", ctypes.c_void_p), ("ldr", ctypes.c_int),
         ("gate_a", ctypes.c_void_p), ("gate_b", ctypes.c_void_p), ("split_row", ctypes.c_int),
         ("alpha", ctypes.c_float), ("row_bias_scale", ctypes.c_void_p),
-        ("qk_cols", ctypes.c_int), ("ln_eps", ctypes.c_float),
-        ("rope_cos", ctypes.c_void_p), ("rope_sin", ctypes.c_void_p),
+        ("qkv_block", ctypes.c_int), ("ln_eps", ctypes.c_float),
+        ("rope_cos", ctypes.c_void_p), ("rope_sin", ctypes.c_void_p), ("rope_row0", ctypes.c_int),
         ("nq_w", ctypes.c_void_p), ("nq_b", ctypes.c_void_p), ("nk_w", ctypes.c_void_p), ("nk_b", ctypes.c_void_p),
+        ("col_block", ctypes.c_int), ("col_block_stride", ctypes.c_longlong),
+        ("a_kblock", ctypes.c_int), ("a_kblock_stride", ctypes.c_longlong),
     ]
 
 

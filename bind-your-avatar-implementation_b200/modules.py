@@ -323,6 +323,23 @@ class AudioProjModel(nn.Module):
         self.norm = nn.LayerNorm(output_dim)
         self.conv1 = nn.Conv1d(context_tokens * output_dim, context_tokens * output_dim, kernel_size=2, stride=2)
 
+    def _conv_weight_as_matrix(self):
+        """conv1 (k=2, s=2) as a [C_out, 2*C_in] matrix over time-major pairs: W2[o, k*C_in + c] = W[o, c, k].
+        Built once per weight version (cuDNN's per-call NCHW->NHWC transform of this 1.2 B-element weight cost
+        ~10 ms per call; as a skinny GEMM the conv is a single pass over the weight)."""
+        w = self.conv1.weight
+        key = (w.data_ptr(), w._version, w.dtype, w.device)
+        if getattr(self, "_w2_key", None) != key:
+            self._w2 = w.detach().permute(0, 2, 1).reshape(w.shape[0], -1).contiguous()
+            self._w2_key = key
+        return self._w2
+
+    def _halve(self, x):
+        """x [R, L, C] time-major -> [R, L/2, C]: Conv1d(k=2, s=2) over the time axis (audio_model.py:98-109)."""
+        R, L, C = x.shape
+        y = F.linear(x.reshape(R * (L // 2), 2 * C), self._conv_weight_as_matrix(), self.conv1.bias)
+        return y.reshape(R, L // 2, C)
+
     def forward(self, audio_embeds):
         R, L = audio_embeds.shape[:2]
         x = audio_embeds.reshape(R * L, -1)
@@ -330,15 +347,10 @@ class AudioProjModel(nn.Module):
         x = torch.relu(self.proj2(x))
         x = self.proj3(x).reshape(R, L, -1)
         for _ in range(2):  # 49 -> 25 -> 13: keep frame 0, halve the rest with the k=2,s=2 conv
-            x = x.permute(0, 2, 1)
-            if x.shape[-1] % 2 == 1:
-                first, rest = x[..., :1], x[..., 1:]
-                if rest.shape[-1] > 0:
-                    rest = self.conv1(rest)
-                x = torch.cat([first, rest], dim=-1)
+            if x.shape[1] % 2 == 1:
+                x = torch.cat([x[:, :1], self._halve(x[:, 1:].contiguous())], dim=1) if x.shape[1] > 1 else x
             else:
-                x = self.conv1(x)
-            x = x.permute(0, 2, 1)
+                x = self._halve(x)
         x = x.reshape(R, x.shape[1], self.context_tokens, self.output_dim)
         return self.norm(x)
 

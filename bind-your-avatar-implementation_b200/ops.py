@@ -44,13 +44,18 @@ def _bf16_2d(t: torch.Tensor, name: str):
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=ACT_NONE, mode=EPI_STORE,
          resid=None, gate_a=None, gate_b=None, split_row=0, alpha=1.0, row_bias_scale=None,
-         qk_cols=0, ln_eps=1e-6, rope=None, nq=None, nk=None, group_m=0) -> torch.Tensor:
-    """out = epilogue(a @ w.T); a [M,K], w [N,K], out [M,N] (row strides may exceed the width)."""
+         qkv_block=0, ln_eps=1e-6, rope=None, rope_row0=0, nq=None, nk=None, group_m=0, col_block=0,
+         col_block_stride=0, a_kblock=0, a_kblock_stride=0) -> torch.Tensor:
+    """out = epilogue(a @ w.T); a [M,K], w [N,K], out [M,N] (row strides may exceed the width).
+    With a_kblock: `a` is the first [M, a_kblock] block of K/a_kblock blocks a_kblock_stride elements apart.
+    With col_block: `out` is the first [M, col_block] block of N/col_block blocks col_block_stride elements apart."""
     global LAUNCHES
     _bf16_2d(a, "a"), _bf16_2d(w, "w"), _bf16_2d(out, "out")
     M, K = a.shape
     N = w.shape[0]
-    if w.shape[1] != K or out.shape[0] != M or out.shape[1] != N:
+    if a_kblock:
+        K = w.shape[1]
+    if w.shape[1] != K or out.shape[0] != M or (out.shape[1] != (col_block if col_block else N)):
         raise RuntimeError(f"bya_b200.gemm: shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
     args = ByaGemmArgs()
     args.M, args.N, args.K = M, N, K
@@ -66,9 +71,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
     args.alpha = alpha
     if mode == EPI_QKV:
         cos, sin = rope
-        args.qk_cols, args.ln_eps = qk_cols, ln_eps
-        args.rope_cos, args.rope_sin = _ptr(cos), _ptr(sin)
+        args.qkv_block, args.ln_eps = qkv_block, ln_eps
+        args.rope_cos, args.rope_sin, args.rope_row0 = _ptr(cos), _ptr(sin), rope_row0
         args.nq_w, args.nq_b, args.nk_w, args.nk_b = _ptr(nq[0]), _ptr(nq[1]), _ptr(nk[0]), _ptr(nk[1])
+    args.col_block, args.col_block_stride = col_block, col_block_stride
+    args.a_kblock, args.a_kblock_stride = a_kblock, a_kblock_stride
     rc = lib().bya_gemm_bf16(_stream(), _ptr(a), a.stride(0), _ptr(w), w.stride(0), ctypes.byref(args))
     check(rc, "gemm")
     LAUNCHES += 1
@@ -181,7 +188,7 @@ def router_head(x, w, b, r, rows, chars):
     return r
 
 
-def xattn_kv32(q, K, Vt, w, out, heads, head_dim, chars, kv_frames, scale):
+def xattn_kv32(q, K, Vt, w, out, heads, head_dim, chars, kv_frames, scale, tok_begin=0, total_tokens=0):
     """Routed 32-key cross-attention; q/out bf16 [tokens, heads*head_dim] views, K [G,H,32,d], Vt [G,H,d,32]."""
     _bf16_2d(q, "q"), _bf16_2d(out, "out"), _f32(w, "w")
     tokens = q.shape[0]
@@ -193,7 +200,8 @@ def xattn_kv32(q, K, Vt, w, out, heads, head_dim, chars, kv_frames, scale):
     if w is not None and tuple(w.shape) != (tokens, chars):
         raise RuntimeError("bya_b200.xattn_kv32: w must be [tokens, chars]")
     rc = lib().bya_xattn_kv32(_stream(), _ptr(q), q.stride(0), _ptr(K), _ptr(Vt), _ptr(w), _ptr(out), out.stride(0),
-                              tokens, heads, head_dim, chars, kv_frames, ctypes.c_float(scale))
+                              tokens, heads, head_dim, chars, kv_frames, ctypes.c_float(scale),
+                              ctypes.c_longlong(tok_begin), ctypes.c_longlong(total_tokens))
     check(rc, "xattn_kv32")
     _count()
     return out

@@ -1,0 +1,69 @@
+"""Sequence-parallel (Ulysses-style) plumbing for the denoising step: one process per GPU, torch.distributed (NCCL over
+NVLink) for the exchanges.  No reference counterpart — the reference is strictly single-GPU; the
+oracle for this path is "same result as one GPU".
+
+Sharding: rank r owns rows [r*N/P, (r+1)*N/P) of the concatenated [text; video] token axis and every weight.
+Per DiT layer two all-to-alls: (1) fused q|k|v, sequence-shard -> head-shard, (2) attention output, head-shard ->
+sequence-shard.  The fused-QKV GEMM writes buffer (1) in its final layout and the out-projection consumes buffer (2) as
+a K-blocked operand (`include/bya.h`: col_block / a_kblock), so no pack or unpack kernel runs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass(frozen=True)
+class RowShard:
+    """This rank's slice of the [text; video] rows."""
+
+    rows: int        # local rows R = N / P
+    first: int       # global index of the first local row
+    text_rows: int   # local rows that are text tokens (they come first)
+    video_rows: int
+    video_first: int  # global video-token index of the first local video row
+
+
+def shard_rows(n_tokens: int, text_len: int, world: int, rank: int) -> RowShard:
+    if n_tokens % world:
+        raise RuntimeError(f"bya_b200: {n_tokens} tokens are not divisible by the sequence-parallel size {world}")
+    R = n_tokens // world
+    n0 = rank * R
+    tl = min(max(text_len - n0, 0), R)
+    return RowShard(R, n0, tl, R - tl, max(n0 - text_len, 0))
+
+
+def qkv_rows_by_destination(w_qkv: torch.Tensor, dim: int, world: int) -> torch.Tensor:
+    """Reorders the rows of the fused [q; k; v] projection ([3*dim, K] or [3*dim]) to [dest rank][q|k|v][heads of dest]."""
+    dl = dim // world
+    return torch.cat([w_qkv[t * dim + r * dl: t * dim + (r + 1) * dl] for r in range(world) for t in range(3)], 0).contiguous()
+
+
+def enable(model, group=None):
+    """Turns on sequence parallelism for `model` over `group` (default: WORLD)."""
+    import torch.distributed as dist
+
+    model._sp_group = group if group is not None else dist.group.WORLD
+    model.invalidate()
+    return model
+
+
+# ---- pure-torch statements of the two exchanges (any backend; used by the gloo tests as the layout specification)
+def exchange_qkv(qkv_send: torch.Tensor, group=None) -> torch.Tensor:
+    """qkv_send [P, R, 3*Dl] ([dest][local row][q|k|v heads of dest]) -> [P*R, 3*Dl]: every row, this rank's heads."""
+    import torch.distributed as dist
+
+    out = torch.empty_like(qkv_send)
+    dist.all_to_all_single(out, qkv_send.contiguous(), group=group)
+    return out.view(-1, qkv_send.shape[-1])
+
+
+def exchange_out(o_send: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """o_send [N, Dl] (every row, this rank's heads) -> [P, R, Dl]: local rows, K-blocked by source rank."""
+    import torch.distributed as dist
+
+    R = o_send.shape[0] // world
+    out = torch.empty(world, R, o_send.shape[1], dtype=o_send.dtype, device=o_send.device)
+    dist.all_to_all_single(out, o_send.contiguous().view(world, R, -1), group=group)
+    return out

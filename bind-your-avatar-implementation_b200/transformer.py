@@ -130,6 +130,7 @@ class BindyouravatarTransformer3DModel(nn.Module):
         self._engine_sig = None
         self._processors: Dict[str, Any] = {}
         self.cache_prologue = True
+        self._sp_group = None  # set by bya_b200.sp.enable(): Ulysses sequence parallelism over this process group
 
     # ------------------------------------------------------------------ reference surface: config / device / dtype
     @property
@@ -240,6 +241,8 @@ class BindyouravatarTransformer3DModel(nn.Module):
         sig = self._signature()
         if self._engine_obj is None or sig != self._engine_sig:
             self._engine_obj = StepEngine(self)
+            if self._sp_group is not None:
+                self._engine_obj.enable_sequence_parallel(self._sp_group)
             self._engine_sig = sig
         return self._engine_obj
 

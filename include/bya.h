@@ -51,14 +51,25 @@ typedef struct ByaGemmArgs {
   int split_row;
   float alpha;
   const float* row_bias_scale; /* [M] or NULL */
-  /* GEMM_EPI_QKV: columns [0, qk_cols) are q|k heads of 64: + bias, LayerNorm(64, ln_eps, affine), RoPE on rows
-   *   >= split_row; columns >= qk_cols (v) only get the bias (diffusers CogVideoXAttnProcessor2_0 as used at
-   *   transformer.py:241-245). */
-  int qk_cols;
+  /* GEMM_EPI_QKV: q and k heads (64 columns each): + bias, LayerNorm(64, ln_eps, affine), RoPE on rows
+   *   >= split_row (rope row = row - split_row + rope_row0); v columns only get the bias (diffusers
+   *   CogVideoXAttnProcessor2_0 as used at transformer.py:241-245). */
+  int qkv_block;          /* width of one [q|k|v] column group (0 -> N); N may hold several groups (one per
+                             sequence-parallel destination rank): within a group the first third is q, the second k */
   float ln_eps;
-  const float* rope_cos;  /* [M - split_row, 64] fp32 */
+  const float* rope_cos;  /* [>= rope_row0 + M - split_row, 64] fp32 */
   const float* rope_sin;
+  int rope_row0;
   const bya_bf16 *nq_w, *nq_b, *nk_w, *nk_b; /* [64] each */
+  /* Sequence-parallel plumbing (no reference counterpart).  Output column-block scatter: column c is
+   * written at out + (c / col_block) * col_block_stride + row * ldc + c % col_block (col_block % 64 == 0; 0 -> off),
+   * i.e. the GEMM writes the all-to-all send buffer [dest][rows][cols_of_dest] directly.  K-blocked A: A is given as
+   * K / a_kblock row-major [M, a_kblock] blocks a_kblock_stride elements apart (the all-to-all receive buffer
+   * [src][rows][cols_of_src]); a_kblock % 64 == 0; 0 -> off. */
+  int col_block;
+  long long col_block_stride;
+  int a_kblock;
+  long long a_kblock_stride;
 } ByaGemmArgs;
 
 int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W, int ldw, const ByaGemmArgs* args);
@@ -77,10 +88,13 @@ int bya_attention_d64(void* stream, const void* q, const void* k, const void* v,
  * w  : [tokens, chars] fp32 routing / audio weights (NULL -> 1).  head_dim in {64,128}, chars in {1,2,3}.
  * Replaces the attention core + routed blend of PerceiverCrossAttention (router.py:256-273 with transformer.py:821-822)
  * and of the audio cross-attention (audio_model.py:253-256 with transformer.py:925-926). */
+/* Sequence-parallel use: q/w/out hold only the `tokens` video tokens [tok_begin, tok_begin+tokens) of `total_tokens`
+ * (total_tokens <= 0 -> tokens are the whole clip, tok_begin ignored). */
 int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* K, const void* Vt, const float* w, void* out,
-                   int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames, float scale);
+                   int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames, float scale,
+                   long long tok_begin, long long total_tokens);
 
-/* Router temporal / multi-ID self-attention (router.py:478-488): n_seq sequences of seq_len (<=32) rows of the
+/* Router temporal / multi-ID self-attention (router.py:478-488): n_seq sequences of seq_len rows of the
  * [rows, 3*heads*64] qkv matrix, rows of one sequence `tok_stride` apart, first row (s/inner)*outer_stride + s%inner. */
 int bya_small_attention(void* stream, const void* qkv, int ld, void* out, int ldo, int n_seq, int seq_len, int heads,
                         int inner, long long outer_stride, long long tok_stride, float scale);

@@ -1,0 +1,291 @@
+"""-m gpu: each sm_100a kernel through the C ABI vs a plain torch fp32 reference of the same op (tolerances stated
+per test: bf16 outputs, fp32 accumulation), incl. ragged / tail shapes; mask path bit-exact vs the C oracle and the
+reference-produced goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+dev = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops(built):
+    import bya_b200  # noqa: F401
+    from bya_b200 import ops as o
+    from bya_b200.lib import lib
+
+    assert torch.cuda.is_available()
+    assert lib().bya_check_device() == 0, "not an sm_100 device / driver entry point missing"
+    return o
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-9))
+
+
+def rnd(*shape, s=1.0):
+    return (torch.randn(*shape, device=dev) * s).bfloat16()
+
+
+# tolerance: outputs are bf16 (rel. spacing 2^-8 = 3.9e-3); inputs bf16-exact, accumulation fp32 -> 1e-2 of abs-max
+TOL = 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,act", [(128, 256, 64, 0), (1000, 768, 1024, 1), (333, 128, 192, 2), (777, 64, 3072, 0),
+                                       (1, 256, 64, 0), (17776, 512, 512, 0)])
+def test_gemm_store(ops, M, N, K, act):
+    torch.manual_seed(1)
+    a, w, b = rnd(M, K, s=0.5), rnd(N, K, s=0.05), rnd(N, s=0.1)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, bias=b, act=act)
+    ref = a.float() @ w.float().t() + b.float()
+    ref = F.gelu(ref, approximate="tanh") if act == 1 else F.gelu(ref) if act == 2 else ref
+    assert rel(out, ref) < TOL
+
+
+def test_gemm_strided_views(ops):
+    """A, out given as column-slice views (row stride > width), as the engine uses them."""
+    torch.manual_seed(2)
+    big = rnd(300, 1024, s=0.5)
+    a = big[:, 256:768]
+    w = rnd(256, 512, s=0.05)
+    outbig = torch.zeros(300, 1024, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, outbig[:, 512:768])
+    assert rel(outbig[:, 512:768], a.float() @ w.float().t()) < TOL
+    assert float(outbig[:, :512].abs().max()) == 0.0
+
+
+def test_gemm_gated_residual(ops):
+    torch.manual_seed(3)
+    M, N, K, split = 1474, 3072, 3072, 226
+    a, w, b, h = rnd(M, K, s=0.5), rnd(N, K, s=0.05), rnd(N, s=0.1), rnd(M, N)
+    ga, gb = torch.randn(N, device=dev), torch.randn(N, device=dev)
+    rbs = torch.rand(M, device=dev) * 2
+    gate = torch.where((torch.arange(M, device=dev) < split)[:, None], ga[None], gb[None])
+    ref = h.float() + 0.7 * gate * (a.float() @ w.float().t() + b.float()[None] * rbs[:, None])
+    out = h.clone()
+    ops.gemm(a, w, out, bias=b, mode=ops.EPI_RESIDUAL, resid=out, gate_a=ga, gate_b=gb, split_row=split, alpha=0.7,
+             row_bias_scale=rbs)
+    assert rel(out, ref) < TOL
+
+
+def test_gemm_qkv_layernorm_rope(ops):
+    torch.manual_seed(4)
+    M, D, K, T = 700, 1024, 512, 226
+    heads = D // 64
+    a, w, b = rnd(M, K, s=0.5), rnd(3 * D, K, s=0.05), rnd(3 * D, s=0.1)
+    nq = [(1 + 0.1 * torch.randn(64, device=dev)).bfloat16(), (0.1 * torch.randn(64, device=dev)).bfloat16()]
+    nk = [(1 + 0.1 * torch.randn(64, device=dev)).bfloat16(), (0.1 * torch.randn(64, device=dev)).bfloat16()]
+    ang = torch.rand(M - T, 32, device=dev) * 6.28
+    cos, sin = ang.cos().repeat_interleave(2, 1).contiguous(), ang.sin().repeat_interleave(2, 1).contiguous()
+    out = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos, sin), nq=nq, nk=nk)
+    y = a.float() @ w.float().t() + b.float()
+
+    def ln_rope(x, g):
+        x = F.layer_norm(x.view(M, heads, 64), (64,), g[0].float(), g[1].float(), 1e-6)
+        xv = x[T:]
+        xr, xi = xv.reshape(M - T, heads, 32, 2).unbind(-1)
+        rot = torch.stack([-xi, xr], -1).flatten(-2)
+        return torch.cat([x[:T], xv * cos[:, None] + rot * sin[:, None]], 0).reshape(M, D)
+
+    ref = torch.cat([ln_rope(y[:, :D], nq), ln_rope(y[:, D:2 * D], nk), y[:, 2 * D:]], 1)
+    assert rel(out, ref) < 1.5e-2
+
+
+def test_gemm_rejects_bad_shapes(ops):
+    a = rnd(128, 100)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, rnd(256, 100), torch.empty(128, 256, device=dev, dtype=torch.bfloat16))  # K % 64 != 0
+    with pytest.raises(RuntimeError):
+        ops.gemm(rnd(128, 64), rnd(100, 64), torch.empty(128, 100, device=dev, dtype=torch.bfloat16))  # N % 64 != 0
+
+
+@pytest.mark.parametrize("batch,seq,heads,qs", [(1, 128, 1, 1.0), (1, 1000, 3, 1.0), (2, 1350, 8, 1.0), (1, 1474, 48, 3.0),
+                                               (3, 70, 2, 1.0), (1, 257, 1, 6.0)])
+def test_attention_d64(ops, batch, seq, heads, qs):
+    """incl. ragged sequence lengths (tail keys masked, tail queries dropped) and large logits (lazy rescale path)."""
+    torch.manual_seed(5)
+    D = heads * 64
+    qkv = rnd(batch * seq, 3 * D, s=qs)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    out = torch.zeros(batch * seq, D, device=dev, dtype=torch.bfloat16)
+    ops.attention_d64(q, k, v, out, batch, seq, heads)
+
+    def hv(x):
+        return x.reshape(batch, seq, heads, 64).transpose(1, 2).float()
+
+    ref = F.scaled_dot_product_attention(hv(q), hv(k), hv(v)).transpose(1, 2).reshape(batch * seq, D)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 2e-2
+
+
+@pytest.mark.parametrize("dim", [512, 768, 1024, 2048, 3072])
+def test_layernorm_modulate(ops, dim):
+    torch.manual_seed(6)
+    rows, split = 300, 37
+    x = rnd(rows, dim, s=2.0) + 0.5
+    g, b = rnd(dim), rnd(dim, s=0.1)
+    sa, ha, sb, hb = (torch.randn(dim, device=dev) * 0.3 for _ in range(4))
+    add = rnd(50, dim)
+    out = torch.empty_like(x)
+    ops.layernorm_modulate(x, out, eps=1e-5, gamma=g, beta=b, mod_a=(sa, ha), mod_b=(sb, hb), split_row=split, add=add)
+    y = F.layer_norm(x.float(), (dim,), g.float(), b.float(), 1e-5)
+    cls = (torch.arange(rows, device=dev) < split)[:, None]
+    y = y * (1 + torch.where(cls, sa[None], sb[None])) + torch.where(cls, ha[None], hb[None])
+    y = y + add.float()[torch.arange(rows, device=dev) % 50]
+    assert rel(out, y) < TOL
+    out2 = torch.empty_like(x)
+    ops.layernorm_modulate(x, out2)  # plain, no affine
+    assert rel(out2, F.layer_norm(x.float(), (dim,))) < TOL
+
+
+def test_gemv_and_timestep_features(ops):
+    torch.manual_seed(7)
+    for B in (1, 2):
+        w, b = rnd(1000, 512, s=0.05), rnd(1000, s=0.1)
+        x = torch.randn(B, 512, device=dev)
+        y = torch.empty(B, 1000, device=dev)
+        ops.gemv(w, b, x, y, in_act=1, out_act=1)
+        ref = F.silu(F.silu(x) @ w.float().t() + b.float())
+        assert float((y - ref).abs().max()) < 1e-4
+    t = torch.tensor([500, 999], device=dev, dtype=torch.int64)
+    out = torch.empty(2, 3072, device=dev)
+    ops.timestep_features(t, out)
+    half = 1536
+    fr = torch.exp(-np.log(10000.0) * torch.arange(half, device=dev, dtype=torch.float32) / half)
+    ang = t[:, None].float() * fr[None]
+    assert float((out - torch.cat([ang.cos(), ang.sin()], -1)).abs().max()) < 2e-4
+
+
+def test_patchify_unpatchify(ops):
+    torch.manual_seed(8)
+    Fr, C, H, W = 3, 48, 16, 24
+    lat = rnd(Fr, C, H, W)
+    out = torch.empty(Fr * (H // 2) * (W // 2), 192, device=dev, dtype=torch.bfloat16)
+    ops.patchify(lat, out)
+    ref = F.unfold(lat.float(), kernel_size=2, stride=2).transpose(1, 2).reshape(-1, C * 4)  # columns (c, dy, dx)
+    assert torch.equal(out.float(), ref)
+    y = rnd(Fr * 8 * 12, 64)
+    img = torch.empty(Fr, 16, 16, 24, device=dev, dtype=torch.bfloat16)
+    ops.unpatchify(y, img)
+    ref = y.reshape(1, Fr, 8, 12, 16, 2, 2).permute(0, 1, 4, 2, 5, 3, 6).flatten(5, 6).flatten(3, 4)[0]
+    assert torch.equal(img, ref)
+
+
+@pytest.mark.parametrize("heads,hd,chars,kvf,tokens", [(16, 128, 2, 1, 1248), (48, 64, 2, 13, 13 * 96), (4, 64, 3, 5, 5 * 37),
+                                                       (2, 128, 1, 1, 50), (3, 128, 3, 2, 2 * 129)])
+def test_routed_cross_attention(ops, heads, hd, chars, kvf, tokens):
+    torch.manual_seed(9)
+    q = rnd(tokens, heads * hd)
+    K = rnd(chars * kvf, heads, 32, hd)
+    V = rnd(chars * kvf, heads, 32, hd)
+    w = torch.rand(tokens, chars, device=dev)
+    out = torch.empty_like(q)
+    scale = hd ** -0.5
+    ops.xattn_kv32(q, K, V.transpose(-1, -2).contiguous(), w, out, heads, hd, chars, kvf, scale)
+    tpf = tokens // kvf
+    qh = q.float().view(kvf, tpf, heads, hd).permute(0, 2, 1, 3)  # [f,h,t,d]
+    ref = torch.zeros(kvf, heads, tpf, hd, device=dev)
+    for c in range(chars):
+        kc, vc = K[c * kvf:(c + 1) * kvf].float(), V[c * kvf:(c + 1) * kvf].float()
+        p = torch.softmax(qh @ kc.transpose(-1, -2) * scale, -1)
+        ref += (p @ vc) * w[:, c].view(kvf, 1, tpf, 1)
+    ref = ref.permute(0, 2, 1, 3).reshape(tokens, heads * hd)
+    assert rel(out, ref) < 1.5e-2
+
+
+def test_router_small_attention_and_head(ops):
+    torch.manual_seed(10)
+    C, Fr, hw, H = 2, 13, 24, 8
+    Nv = Fr * hw
+    qkv = rnd(C * Nv, 1536)
+    out = torch.zeros(C * Nv, 512, device=dev, dtype=torch.bfloat16)
+    # temporal: sequences of the Fr tokens at one (c, hw)
+    ops.small_attention(qkv, out, C * hw, Fr, H, hw, Nv, hw)
+    x = qkv.float().view(C, Fr, hw, 3, H, 64)
+    q, k, v = (x[:, :, :, i].permute(0, 2, 3, 1, 4) for i in range(3))  # [C,hw,H,Fr,64]
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 3, 1, 2, 4).reshape(C * Nv, 512)
+    assert rel(out, ref) < TOL
+    # multi-ID: sequences of the C tokens at one n
+    ops.small_attention(qkv, out, Nv, C, H, Nv, 0, Nv)
+    x = qkv.float().view(C, Nv, 3, H, 64)
+    q, k, v = (x[:, :, i].permute(1, 2, 0, 3) for i in range(3))  # [Nv,H,C,64]
+    ref = F.scaled_dot_product_attention(q, k, v).permute(2, 0, 1, 3).reshape(C * Nv, 512)
+    assert rel(out, ref) < TOL
+    xh, w, b = rnd(C * Nv, 512), rnd(512, s=0.1), rnd(1)
+    r = torch.empty(Nv, C, device=dev)
+    ops.router_head(xh, w, b, r, Nv, C)
+    ref = torch.sigmoid(xh.float() @ w.float() + b.float()).view(C, Nv).t()
+    assert float((r - ref).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ bit-exact mask path
+def _c_oracle(masks, Fr, gh, gw, frame_or=False):
+    import ctypes
+
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libmask_oracle.so"))
+    C, T, H, W = masks.shape
+    n = Fr * gh * gw
+    idx, lg = np.zeros(n, np.int64), np.zeros((n, C), np.float32)
+    m = np.ascontiguousarray(masks, np.uint8)
+    lib.bya_oracle_masks_to_routing(m.ctypes.data_as(ctypes.c_void_p), C, T, H, W, Fr, gh, gw,
+                                    idx.ctypes.data_as(ctypes.c_void_p), lg.ctypes.data_as(ctypes.c_void_p), int(frame_or))
+    return idx, lg
+
+
+@pytest.mark.parametrize("kind", ["moving", "static", "overlap", "speckle"])
+def test_masks_to_routing_bit_exact_vs_reference_golden(ops, kind):
+    import bya_b200  # noqa: F401
+    from bya_b200.synth import tracking_masks
+
+    g = torch.load(os.path.join(GOLD, f"masks_{kind}.pt"))
+    masks = tracking_masks(kind)
+    idx, lg = ops.masks_to_routing(torch.from_numpy(masks).to(dev), 13, 30, 45)
+    assert torch.equal(lg.cpu(), g["routing_logits"][0].float())  # reference's own output, bit for bit
+    ci, cl = _c_oracle(masks, 13, 30, 45)
+    assert np.array_equal(idx.cpu().numpy(), ci) and np.array_equal(lg.cpu().numpy(), cl)
+    ored = ops.routing_frame_or(lg, torch.empty_like(lg), 13)
+    assert np.array_equal(ored.cpu().numpy(), _c_oracle(masks, 13, 30, 45, frame_or=True)[1])
+
+
+@pytest.mark.parametrize("geom", [(3, 97, 200, 300, 25, 10, 15), (2, 49, 480, 720, 13, 30, 45), (1, 13, 30, 45, 13, 30, 45),
+                                  (3, 10, 33, 47, 13, 8, 12), (2, 1, 4, 4, 1, 1, 1)])
+def test_masks_to_routing_bit_exact_random_geometries(ops, geom):
+    """3 characters, 97 frames, non-integer scales, identity and degenerate sizes; random speckle maximises ties."""
+    C, T, H, W, Fr, gh, gw = geom
+    rng = np.random.RandomState(11)
+    masks = (rng.rand(C, T, H, W) > 0.5).astype(np.uint8) * rng.randint(1, 255, size=(C, 1, 1, 1)).astype(np.uint8)
+    idx, lg = ops.masks_to_routing(torch.from_numpy(masks).to(dev), Fr, gh, gw)
+    ci, cl = _c_oracle(masks, Fr, gh, gw)
+    assert np.array_equal(idx.cpu().numpy(), ci) and np.array_equal(lg.cpu().numpy(), cl)
+    # empty masks -> all background
+    idx0, lg0 = ops.masks_to_routing(torch.zeros_like(torch.from_numpy(masks)).to(dev), Fr, gh, gw)
+    assert int((idx0 != -1).sum()) == 0 and float(lg0.abs().sum()) == 0.0
+
+
+def test_audio_weights_exact_for_hard_masks(ops):
+    from oracle import restated
+
+    torch.manual_seed(12)
+    for C in (2, 3):
+        lab = torch.randint(-1, C, (500,))
+        r = torch.zeros(500, C)
+        for c in range(C):
+            r[lab == c, c] = 1
+        for af in (torch.eye(C), (1 - torch.eye(C)) if C == 2 else torch.eye(C)[[1, 2, 0]]):
+            w = torch.empty(500, C, device=dev)
+            ws = torch.empty(500, device=dev)
+            ops.audio_weights(af.to(dev).contiguous(), r.to(dev), w, ws)
+            ref = restated.audio_weights(af, r)
+            assert torch.equal(w.cpu(), ref) and torch.equal(ws.cpu(), ref.sum(1))
+    r = torch.rand(300, 2)
+    w = torch.empty(300, 2, device=dev)
+    ops.audio_weights(torch.eye(2, device=dev), r.to(dev), w)
+    assert float((w.cpu() - (1 - r[:, [1, 0]])).abs().max()) < 1e-6

@@ -1,0 +1,88 @@
+"""world_size-2 gloo tests (CPU) of the sequence-parallel host logic: row sharding arithmetic, the [dest][rows][q|k|v]
+send layout + all-to-all, and the K-blocked out-projection — equal to the single-process result."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_rows_covers_everything():
+    sys.path.insert(0, ROOT)
+    import bya_b200  # noqa: F401
+    from bya_b200.sp import shard_rows
+
+    for N, T in ((17776, 226), (33976, 226), (1474, 226)):
+        for P in (1, 2, 4, 8):
+            if N % P:
+                with pytest.raises(RuntimeError):
+                    shard_rows(N, T, P, 0)
+                continue
+            tot_t = tot_v = 0
+            nxt_v = 0
+            for r in range(P):
+                s = shard_rows(N, T, P, r)
+                assert s.rows == N // P and s.text_rows + s.video_rows == s.rows and s.first == r * s.rows
+                assert s.video_first == nxt_v
+                nxt_v += s.video_rows
+                tot_t += s.text_rows
+                tot_v += s.video_rows
+            assert tot_t == T and tot_v == N - T
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import bya_b200  # noqa: F401
+    from bya_b200.sp import exchange_out, exchange_qkv, qkv_rows_by_destination, shard_rows
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)  # identical on every rank
+        N, T, D, heads = 40, 6, 256, 4
+        Dl = D // world
+        x = torch.randn(N, D)
+        w_qkv, b_qkv = torch.randn(3 * D, D) * 0.1, torch.randn(3 * D) * 0.1
+        w_o = torch.randn(D, D) * 0.1
+        # single-process truth
+        qkv = x @ w_qkv.t() + b_qkv
+
+        def hv(t):
+            return t.view(N, heads, 64).transpose(0, 1)
+
+        o = torch.nn.functional.scaled_dot_product_attention(hv(qkv[:, :D]), hv(qkv[:, D:2 * D]), hv(qkv[:, 2 * D:]))
+        truth = o.transpose(0, 1).reshape(N, D) @ w_o.t()
+        # sequence-parallel: local rows, fused projection with destination-ordered columns
+        sh = shard_rows(N, T, world, rank)
+        xl = x[sh.first: sh.first + sh.rows]
+        w_sp, b_sp = qkv_rows_by_destination(w_qkv, D, world), qkv_rows_by_destination(b_qkv, D, world)
+        y = xl @ w_sp.t() + b_sp                                   # [R, P*3*Dl], column groups per destination
+        send = y.view(sh.rows, world, 3 * Dl).transpose(0, 1).contiguous()   # what the GEMM's col_block scatter writes
+        full = exchange_qkv(send)                                  # [N, 3*Dl]: every row, my heads
+        hl = heads // world
+
+        def hvl(t):
+            return t.reshape(N, hl, 64).transpose(0, 1)
+
+        ol = torch.nn.functional.scaled_dot_product_attention(hvl(full[:, :Dl]), hvl(full[:, Dl:2 * Dl]), hvl(full[:, 2 * Dl:]))
+        o_send = ol.transpose(0, 1).reshape(N, Dl)
+        blocks = exchange_out(o_send, world)                       # [P, R, Dl]
+        mine = sum(blocks[s] @ w_o[:, s * Dl:(s + 1) * Dl].t() for s in range(world))   # K-blocked A operand
+        err = float((mine - truth[sh.first: sh.first + sh.rows]).abs().max())
+        ret[rank] = err
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ulysses_exchange_layouts_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world and all(v < 1e-4 for v in ret.values()), dict(ret)

@@ -56,7 +56,7 @@ def test_qkv(M, D, K, T):
     ang = torch.rand(M - T, 32, device=dev) * 6.28
     cos = ang.cos().repeat_interleave(2, 1).contiguous(); sin = ang.sin().repeat_interleave(2, 1).contiguous()
     out = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
-    ops.gemm(a, w, out, bias=b, mode=ops.EPI_QKV, split_row=T, qk_cols=2 * D, ln_eps=1e-6, rope=(cos, sin), nq=nq, nk=nk)
+    ops.gemm(a, w, out, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos, sin), nq=nq, nk=nk)
     torch.cuda.synchronize()
     y = a.float() @ w.float().t() + b.float()
     q, k, v = y[:, :D], y[:, D:2 * D], y[:, 2 * D:]

@@ -1,0 +1,34 @@
+"""torchrun --nproc-per-node P tools/gpu_check_sp.py : sequence-parallel step == single-GPU step (same kernels)."""
+import os, sys, dataclasses
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+import bya_b200
+from bya_b200 import sp
+from bya_b200.synth import CONFIGS, make_inputs
+from bench import build_model
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+ok = True
+for forced in (False, True):
+    cfg = dataclasses.replace(CONFIGS["c1"], num_layers=2, grid_h=6, grid_w=9, cross_attn_interval=2)  # 928 tokens = 8 * 116
+    model = build_model(cfg, dev)
+    inp = make_inputs(cfg, 1234, device=dev, dtype=torch.bfloat16, forced_masks=forced)
+    ref = model(**inp)[0].float()
+    sp.enable(model)
+    out = model(**inp)[0].float()
+    a, b = out.flatten().double(), ref.flatten().double()
+    cos = float((a @ b) / (a.norm() * b.norm()))
+    err = float((out - ref).abs().max())
+    print(f"rank {rank}/{world} forced={forced}: cos={cos:.7f} max_abs={err:.4e} ref_absmax={float(ref.abs().max()):.3f}", flush=True)
+    ok &= cos > 0.9999 and err < 0.05 * float(ref.abs().max())
+    del model
+t = torch.tensor([1.0 if ok else 0.0], device=dev)
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("SP OK" if t.item() == 1.0 else "SP FAILED", flush=True)
+dist.destroy_process_group()
