@@ -178,6 +178,12 @@ BYA_DEVICE uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
 }
 
 // TMEM -> registers: this thread's lane (32*(warp%4)+laneid), N consecutive 32-bit columns.
+BYA_DEVICE void tmem_ld_x1(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
+}
+BYA_DEVICE void tmem_st_x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
 BYA_DEVICE void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])

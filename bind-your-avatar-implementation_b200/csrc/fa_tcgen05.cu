@@ -25,7 +25,8 @@ constexpr int FA_BN = 128;         // keys per KV tile
 constexpr int FA_STAGES = 4;       // K ring depth == V ring depth
 constexpr int FA_THREADS = 384;
 constexpr int FA_TILE_BYTES = FA_BM * FA_D * 2;  // 16 KB
-constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + 512 + 1024;
+constexpr int FA_ONES_BYTES = 2048;             // [16 x 64] bf16 ones: B operand of the row-sum MMA
+constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + FA_ONES_BYTES + 512 + 1024;
 
 struct FaArgs {
   int seq;        // rows per batch element (queries == keys)
@@ -41,6 +42,22 @@ BYA_DEVICE void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32
 template <int R>
 BYA_DEVICE void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
+BYA_DEVICE float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// (t0, t1) = (a0, a1) * c + d   as one packed FFMA2
+BYA_DEVICE void fma2(float& t0, float& t1, float a0, float a1, float c, float d) {
+  asm("{\n\t.reg .b64 va, vc, vd;\n\t"
+      "mov.b64 va, {%2, %3};\n\t"
+      "mov.b64 vc, {%4, %4};\n\t"
+      "mov.b64 vd, {%5, %5};\n\t"
+      "fma.rn.f32x2 va, va, vc, vd;\n\t"
+      "mov.b64 {%0, %1}, va;\n\t}\n"
+      : "=f"(t0), "=f"(t1)
+      : "f"(a0), "f"(a1), "f"(c), "f"(d));
+}
 BYA_DEVICE float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -55,7 +72,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint8_t* sQ = smem;                                   // [2][16 KB]
   uint8_t* sK = smem + 2 * FA_TILE_BYTES;               // [STAGES][16 KB]
   uint8_t* sV = sK + FA_STAGES * FA_TILE_BYTES;         // [STAGES][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_TILE_BYTES);
+  uint8_t* sOnes = sV + FA_STAGES * FA_TILE_BYTES;      // [2 KB] bf16 1.0 (any swizzle of all-ones is all-ones)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + FA_ONES_BYTES);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* k_full = bars + 1;             // [STAGES]
   uint64_t* k_empty = k_full + FA_STAGES;  // [STAGES]
@@ -95,12 +113,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
+  for (int i = threadIdx.x; i < FA_ONES_BYTES / 4; i += FA_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+  fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384);  P_t overwrites S_t[0,64) as packed bf16
-  constexpr uint32_t kColS = 0, kColO = 256;
+  // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)  L0 [384,400)  L1 [400,416);
+  // P_t overwrites S_t[0,64) as packed bf16; L_t = P_t * ones accumulates the softmax row sums on the tensor pipe
+  constexpr uint32_t kColS = 0, kColO = 256, kColL = 384;
 
   if (warp < 4) {
     setmaxnreg_dec<56>();
@@ -126,6 +147,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       // ---------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, FA_D, 0, 1);  // B = V is MN-major (d contiguous)
+      constexpr uint32_t idesc_pl = make_idesc_bf16(FA_BM, 16, 0, 0);    // B = ones [16 x K], K-major
+      const uint64_t d_ones = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
       const uint32_t q_addr = smem_u32(sQ);
       auto issue_qk = [&](int t, int stage) {
         const uint64_t da = make_smem_desc_sw128(q_addr + t * FA_TILE_BYTES, 16, 1024);
@@ -137,9 +160,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       auto issue_pv = [&](int t, int stage, bool acc) {
         const uint64_t db = make_smem_desc_sw128(smem_u32(sV + stage * FA_TILE_BYTES), 1024, 1024);
 #pragma unroll
-        for (int k = 0; k < FA_BN / 16; ++k)
+        for (int k = 0; k < FA_BN / 16; ++k) {
           umma_ts(tmem_base + kColO + t * 64, tmem_base + kColS + t * 128 + k * 8, db + uint64_t(128 * k), idesc_pv,
                   acc || k != 0);
+          umma_ts(tmem_base + kColL + t * 16, tmem_base + kColS + t * 128 + k * 8, d_ones, idesc_pl, acc || k != 0);
+        }
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
@@ -199,8 +224,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const uint32_t tS = tmem_base + kColS + t * 128 + lane_off;
     const uint32_t tO = tmem_base + kColO + t * 64 + lane_off;
+    const uint32_t tL = tmem_base + kColL + t * 16 + lane_off;
     const float c = p.scale_log2;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
@@ -218,11 +244,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        mx[0] = fmaxf(mx[0], __uint_as_float(s[i]));
-        mx[1] = fmaxf(mx[1], __uint_as_float(s[i + 1]));
-        mx[2] = fmaxf(mx[2], __uint_as_float(s[i + 2]));
-        mx[3] = fmaxf(mx[3], __uint_as_float(s[i + 3]));
+      for (int i = 0; i < 128; i += 8) {
+        mx[0] = max3(mx[0], __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mx[1] = max3(mx[1], __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mx[2] = max3(mx[2], __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mx[3] = max3(mx[3], __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
       }
       const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       if (j == 0) {
@@ -233,34 +259,28 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const float mn = fmaxf(m, mt);
           const float alpha = ex2((m - mn) * c);
           m = mn;
-          l *= alpha;
           uint32_t o[64];
           tmem_ld_x32(tO, o);
           tmem_ld_x32(tO + 32, o + 32);
+          uint32_t lsum;
+          tmem_ld_x1(tL, &lsum);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 64; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          lsum = __float_as_uint(__uint_as_float(lsum) * alpha);
           tmem_st_x32(tO, o);
           tmem_st_x32(tO + 32, o + 32);
+          tmem_st_x1(tL, lsum);
         }
       }
-      const float mc = m * c;
-      float sum[4] = {0.f, 0.f, 0.f, 0.f};
+      const float nmc = -m * c;
       uint32_t pk[64];
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        const float p0 = ex2(fmaf(__uint_as_float(s[i]), c, -mc));
-        const float p1 = ex2(fmaf(__uint_as_float(s[i + 1]), c, -mc));
-        const float p2 = ex2(fmaf(__uint_as_float(s[i + 2]), c, -mc));
-        const float p3 = ex2(fmaf(__uint_as_float(s[i + 3]), c, -mc));
-        sum[0] += p0;
-        sum[1] += p1;
-        sum[2] += p2;
-        sum[3] += p3;
-        pk[i / 2] = pack_bf16x2(p0, p1);
-        pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+      for (int i = 0; i < 128; i += 2) {
+        float t0, t1;
+        fma2(t0, t1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, nmc);
+        pk[i / 2] = pack_bf16x2(ex2(t0), ex2(t1));
       }
-      l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
       tmem_st_x32(tS, pk);
       tmem_st_x32(tS + 32, pk + 32);
       tmem_st_wait();
@@ -274,9 +294,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     tmem_ld_x32(tO, o);
     tmem_ld_x32(tO + 32, o + 32);
     tmem_ld_wait();
+    uint32_t lbits;
+    tmem_ld_x1(tL, &lbits);
+    tmem_ld_wait();
     const int qrow = q0 + t * FA_BM + q * 32 + lane;
     if (qrow < p.seq) {
-      const float inv = 1.0f / l;
+      const float inv = 1.0f / __uint_as_float(lbits);
       uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row_base + qrow) * p.ldo + col);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {

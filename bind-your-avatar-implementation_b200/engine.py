@@ -413,7 +413,7 @@ class StepEngine:
                     tap(f"block{i}.video", xv)
                     tap(f"block{i}.text", x[:T])
                 # ---- face cross-attention + routing (transformer.py:737-833)
-                if m.is_train_face and i % m.cross_attn_interval == 0:
+                if m.is_train_face and i % m.cross_attn_interval == 0 and ca < len(self.face):
                     Fc = self.face[ca]
                     dq = Fc["w_q"].shape[0]
                     qpad = ws.get("face_q", (R, dq))         # rows [Tl:] hold the local video queries
