@@ -5,17 +5,27 @@
 // (models/router.py:474-476, K10).  Q/K/V are read in place from the (fused) projection output — row-major
 // [rows, ld] with head h at columns h*64.. — so no head-major copy is ever made.
 //
-// One CTA = one (batch, head, 256 query rows).  Warp roles:
-//   warp 0       TMA producer: Q (2 x 128 rows) once, then a ring of K and V tiles (128 keys each)
-//   warp 1       MMA issuer:   S_t = Q_t K^T (tcgen05.mma SS, fp32 in TMEM), O_t += P_t V (tcgen05.mma TS, P read
-//                              from TMEM where the softmax warps wrote it over S_t)
+// One CTA = one (batch, head, 256 query rows) = two 128-row query tiles; KV tiles of 128 keys.  Warp roles:
+//   warp 0       TMA producer (one thread): Q once, then 4-deep rings of K and V tiles
+//   warp 1       MMA issuer (one thread):   S_t = Q_t K^T (tcgen05.mma SS, fp32 in TMEM),
+//                                           O_t += P_t V  (tcgen05.mma TS: P read from TMEM, V consumed MN-major
+//                                           straight from its natural [key, d] layout)
 //   warp 2       TMEM allocator
 //   warps 4-7    softmax for query tile 0   (one thread per query row; tcgen05.ld S -> exp2 -> tcgen05.st P)
 //   warps 8-11   softmax for query tile 1
-// The two query tiles ping-pong on the tensor pipe: while one tile's softmax runs, the other's MMAs issue.
-// Running max uses lazy rescaling (O in TMEM is only rescaled when the max grows by more than 2^8).
+// TMEM (512 columns): S_t [128t, 128t+128)   P_t [256+64t, +64) (packed bf16)   O_t [384+64t, +64).
+// S and P live in DIFFERENT columns, so the softmax warps hand S back (`s_free`) as soon as the scores are in
+// registers and Q K^T of KV tile j+1 runs on the tensor pipe while the exponentials of tile j are being computed:
+// in steady state neither side waits for the other (the round-1 profile had the softmax warps waiting on `s_full`
+// for 29 % of their time and the single MMA warp spending 2/3 of its time on loop overhead).
+// d=64 attention is exp-bound (16 ex2/clk/SM vs 8192 MMA-FLOP/clk/SM): FA_POLY16 of every 16 exponentials are
+// evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel. error 8.8e-5, far below the
+// bf16 rounding of P) instead of MUFU.EX2.  Row sums are accumulated in registers with packed f32x2 adds; the
+// running max uses lazy rescaling (O in TMEM is only rescaled when the max grows by more than 2^8).
 #include "common.cuh"
 #include "../../include/bya.h"
+
+#include <cstdlib>
 
 namespace bya {
 
@@ -25,8 +35,7 @@ constexpr int FA_BN = 128;         // keys per KV tile
 constexpr int FA_STAGES = 4;       // K ring depth == V ring depth
 constexpr int FA_THREADS = 384;
 constexpr int FA_TILE_BYTES = FA_BM * FA_D * 2;  // 16 KB
-constexpr int FA_ONES_BYTES = 2048;             // [16 x 64] bf16 ones: B operand of the row-sum MMA
-constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + FA_ONES_BYTES + 512 + 1024;
+constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + 512 + 1024;
 
 struct FaArgs {
   int seq;        // rows per batch element (queries == keys)
@@ -34,6 +43,7 @@ struct FaArgs {
   int batch;
   int ldo;        // row stride of O in elements
   float scale_log2;  // softmax scale * log2(e)
+  int skew_cycles;   // start delay of the tile-1 softmax warps (see the kernel)
   __nv_bfloat16* out;
 };
 
@@ -58,34 +68,89 @@ BYA_DEVICE void fma2(float& t0, float& t1, float a0, float a1, float c, float d)
       : "=f"(t0), "=f"(t1)
       : "f"(a0), "f"(a1), "f"(c), "f"(d));
 }
+// (t0, t1) = (a0, a1) * (b0, b1) + c
+BYA_DEVICE void fma2v(float& t0, float& t1, float a0, float a1, float b0, float b1, float c) {
+  asm("{\n\t.reg .b64 va, vb, vc;\n\t"
+      "mov.b64 va, {%2, %3};\n\t"
+      "mov.b64 vb, {%4, %5};\n\t"
+      "mov.b64 vc, {%6, %6};\n\t"
+      "fma.rn.f32x2 va, va, vb, vc;\n\t"
+      "mov.b64 {%0, %1}, va;\n\t}\n"
+      : "=f"(t0), "=f"(t1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c));
+}
+// (a0, a1) += (b0, b1)
+BYA_DEVICE void add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 va, vb;\n\t"
+      "mov.b64 va, {%0, %1};\n\t"
+      "mov.b64 vb, {%2, %3};\n\t"
+      "add.rn.f32x2 va, va, vb;\n\t"
+      "mov.b64 {%0, %1}, va;\n\t}\n"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
 BYA_DEVICE float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): x = n + f, n = floor(x) via a round-down magic add,
+// 2^f ~ degree-3 minimax polynomial on [0,1), exponent patched in with one integer shift-add.
+BYA_DEVICE void ex2_poly2(float& y0, float& y1, float x0, float x1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  float t0, t1, n0, n1, f0, f1, p0, p1;
+  asm("{\n\t.reg .b64 va, vb;\n\t"
+      "mov.b64 va, {%2, %3};\n\t"
+      "mov.b64 vb, {%4, %4};\n\t"
+      "add.rm.ftz.f32x2 va, va, vb;\n\t"
+      "mov.b64 {%0, %1}, va;\n\t}\n"
+      : "=f"(t0), "=f"(t1)
+      : "f"(x0), "f"(x1), "f"(12582912.0f));
+  asm("{\n\t.reg .b64 va, vb;\n\t"
+      "mov.b64 va, {%2, %3};\n\t"
+      "mov.b64 vb, {%4, %4};\n\t"
+      "add.rn.ftz.f32x2 va, va, vb;\n\t"
+      "mov.b64 {%0, %1}, va;\n\t}\n"
+      : "=f"(n0), "=f"(n1)
+      : "f"(t0), "f"(t1), "f"(-12582912.0f));
+  asm("{\n\t.reg .b64 va, vb;\n\t"
+      "mov.b64 va, {%2, %3};\n\t"
+      "mov.b64 vb, {%4, %5};\n\t"
+      "sub.rn.ftz.f32x2 va, va, vb;\n\t"
+      "mov.b64 {%0, %1}, va;\n\t}\n"
+      : "=f"(f0), "=f"(f1)
+      : "f"(x0), "f"(x1), "f"(n0), "f"(n1));
+  fma2v(p0, p1, f0, f1, 0.0771190897f, 0.0771190897f, 0.2275643945f);
+  fma2v(p0, p1, p0, p1, f0, f1, 0.6951461434f);
+  fma2v(p0, p1, p0, p1, f0, f1, 1.0f);
+  y0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
 
+template <int POLY16>   // POLY16: exponentials per group of 16 evaluated by ex2_poly2 (0,4,8,12)
 __global__ void __launch_bounds__(FA_THREADS, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const __grid_constant__ CUtensorMap tmap_v, const FaArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [2][16 KB]
-  uint8_t* sK = smem + 2 * FA_TILE_BYTES;               // [STAGES][16 KB]
+  uint8_t* sK = sQ + 2 * FA_TILE_BYTES;                 // [STAGES][16 KB]
   uint8_t* sV = sK + FA_STAGES * FA_TILE_BYTES;         // [STAGES][16 KB]
-  uint8_t* sOnes = sV + FA_STAGES * FA_TILE_BYTES;      // [2 KB] bf16 1.0 (any swizzle of all-ones is all-ones)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + FA_ONES_BYTES);
-  uint64_t* q_full = bars;                 // [1]
-  uint64_t* k_full = bars + 1;             // [STAGES]
-  uint64_t* k_empty = k_full + FA_STAGES;  // [STAGES]
-  uint64_t* v_full = k_empty + FA_STAGES;
-  uint64_t* v_empty = v_full + FA_STAGES;
-  uint64_t* s_full = v_empty + FA_STAGES;  // [2]
-  uint64_t* p_full = s_full + 2;           // [2]
-  uint64_t* o_full = p_full + 2;           // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_TILE_BYTES);
+  uint64_t* q_full = bars;                    // [1]
+  uint64_t* k_full = q_full + 1;              // [STAGES]
+  uint64_t* k_empty = k_full + FA_STAGES;     // [STAGES]
+  uint64_t* v_full = k_empty + FA_STAGES;     // [STAGES]
+  uint64_t* v_empty = v_full + FA_STAGES;     // [STAGES]
+  uint64_t* s_full = v_empty + FA_STAGES;     // [2]  S_t(j) = Q_t K(j)^T landed in TMEM
+  uint64_t* s_free = s_full + 2;              // [2]  S_t(j) is in the softmax registers: S_t may be overwritten
+  uint64_t* p_full = s_free + 2;              // [2]  P_t(j) written to TMEM
+  uint64_t* pv_done = p_full + 2;             // [2]  O_t += P_t(j) V(j) complete: P_t free, O_t stable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform: role/TMEM addresses
+  const int lane = threadIdx.x & 31;                                // stay in uniform registers
   const int qblk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int row_base = b * p.seq;               // first row of this batch element in the [rows, ld] matrices
   const int q0 = qblk * (2 * FA_BM);            // first query row (within the batch element)
@@ -107,113 +172,126 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&s_free[t], 4);    // one arrive per softmax warp
+      mbar_init(&p_full[t], 4);
+      mbar_init(&pv_done[t], 1);
     }
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
-  for (int i = threadIdx.x; i < FA_ONES_BYTES / 4; i += FA_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
-  fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)  L0 [384,400)  L1 [400,416);
-  // P_t overwrites S_t[0,64) as packed bf16; L_t = P_t * ones accumulates the softmax row sums on the tensor pipe
-  constexpr uint32_t kColS = 0, kColO = 256, kColL = 384;
+  constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
 
   if (warp < 4) {
     setmaxnreg_dec<56>();
     if (warp == 0) {
-      // ---------------------------------------------------------------- TMA producer
+      // ---------------------------------------------------------------- TMA producer (one elected thread)
       if (elect_one()) {
         mbar_arrive_expect_tx(q_full, 2 * FA_TILE_BYTES);
         tma_load_2d(sQ, &tmap_q, q_full, col, row_base + q0, kEvictFirst);
         tma_load_2d(sQ + FA_TILE_BYTES, &tmap_q, q_full, col, row_base + q0 + FA_BM, kEvictFirst);
-        int stage = 0;
-        uint32_t phase = 0;
+        // order: K(0), then K(j+1), V(j): K runs one tile ahead because S(j+1) is computed before O += P(j) V(j)
+        mbar_arrive_expect_tx(&k_full[0], FA_TILE_BYTES);
+        tma_load_2d(sK, &tmap_k, &k_full[0], col, row_base, kEvictLast);
+        int ks = 1, vs = 0;
+        uint32_t kph = 0, vph = 0;
         for (int j = 0; j < n_kv; ++j) {
-          mbar_wait(&k_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&k_full[stage], FA_TILE_BYTES);
-          tma_load_2d(sK + stage * FA_TILE_BYTES, &tmap_k, &k_full[stage], col, row_base + j * FA_BN, kEvictLast);
-          mbar_wait(&v_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&v_full[stage], FA_TILE_BYTES);
-          tma_load_2d(sV + stage * FA_TILE_BYTES, &tmap_v, &v_full[stage], col, row_base + j * FA_BN, kEvictLast);
-          if (++stage == FA_STAGES) { stage = 0; phase ^= 1; }
+          if (j + 1 < n_kv) {
+            mbar_wait(&k_empty[ks], kph ^ 1);
+            mbar_arrive_expect_tx(&k_full[ks], FA_TILE_BYTES);
+            tma_load_2d(sK + ks * FA_TILE_BYTES, &tmap_k, &k_full[ks], col, row_base + (j + 1) * FA_BN, kEvictLast);
+            if (++ks == FA_STAGES) { ks = 0; kph ^= 1; }
+          }
+          mbar_wait(&v_empty[vs], vph ^ 1);
+          mbar_arrive_expect_tx(&v_full[vs], FA_TILE_BYTES);
+          tma_load_2d(sV + vs * FA_TILE_BYTES, &tmap_v, &v_full[vs], col, row_base + j * FA_BN, kEvictLast);
+          if (++vs == FA_STAGES) { vs = 0; vph ^= 1; }
         }
       }
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer
+      // The whole warp runs the warp-uniform loop and polls the barriers; one elected lane issues (ptxas keeps
+      // descriptors in uniform registers only when control flow is provably uniform).
       constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, FA_D, 0, 1);  // B = V is MN-major (d contiguous)
-      constexpr uint32_t idesc_pl = make_idesc_bf16(FA_BM, 16, 0, 0);    // B = ones [16 x K], K-major
-      const uint64_t d_ones = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
-      const uint32_t q_addr = smem_u32(sQ);
-      auto issue_qk = [&](int t, int stage) {
-        const uint64_t da = make_smem_desc_sw128(q_addr + t * FA_TILE_BYTES, 16, 1024);
-        const uint64_t db = make_smem_desc_sw128(smem_u32(sK + stage * FA_TILE_BYTES), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k)
-          umma_ss(tmem_base + kColS + t * 128, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc_qk, k != 0);
-      };
-      auto issue_pv = [&](int t, int stage, bool acc) {
-        const uint64_t db = make_smem_desc_sw128(smem_u32(sV + stage * FA_TILE_BYTES), 1024, 1024);
-#pragma unroll
-        for (int k = 0; k < FA_BN / 16; ++k) {
-          umma_ts(tmem_base + kColO + t * 64, tmem_base + kColS + t * 128 + k * 8, db + uint64_t(128 * k), idesc_pv,
-                  acc || k != 0);
-          umma_ts(tmem_base + kColL + t * 16, tmem_base + kColS + t * 128 + k * 8, d_ones, idesc_pl, acc || k != 0);
-        }
-      };
+      const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t dq1 = make_smem_desc_sw128(smem_u32(sQ + FA_TILE_BYTES), 16, 1024);
+      const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV), 1024, 1024);
+      constexpr uint64_t kStageStep = FA_TILE_BYTES >> 4;   // descriptor address field is in 16 B units
+      const uint32_t tS0 = tmem_base + kColS, tS1 = tmem_base + kColS + 128;
+      const uint32_t tP0 = tmem_base + kColP, tP1 = tmem_base + kColP + 64;
+      const uint32_t tO0 = tmem_base + kColO, tO1 = tmem_base + kColO + 64;
+
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       if (elect_one()) {
-        issue_qk(0, 0);
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k) umma_ss(tS0, dq0 + uint64_t(2 * k), dk0 + uint64_t(2 * k), idesc_qk, k != 0);
         umma_commit(&s_full[0]);
-        issue_qk(1, 0);
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k) umma_ss(tS1, dq1 + uint64_t(2 * k), dk0 + uint64_t(2 * k), idesc_qk, k != 0);
         umma_commit(&s_full[1]);
         umma_commit(&k_empty[0]);
       }
       __syncwarp();
-      int stage = 0;
-      uint32_t phase = 0;
+      int ks = 1, vs = 0;          // ring slots of K(j+1) and V(j)
+      uint32_t kph = 0, vph = 0;
       for (int j = 0; j < n_kv; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == FA_STAGES) { nstage = 0; nphase ^= 1; }
-        const bool more = (j + 1 < n_kv);
-        mbar_wait(&v_full[stage], phase);
-        mbar_wait(&p_full[0], j & 1);
-        tc_fence_after();
-        if (elect_one()) issue_pv(0, stage, j > 0);
-        __syncwarp();
-        if (more) {
-          mbar_wait(&k_full[nstage], nphase);
+        const uint32_t jp = j & 1;
+        if (j + 1 < n_kv) {
+          // S_t(j+1) = Q_t K(j+1)^T as soon as the softmax warps hold S_t(j) in registers
+          const uint64_t dk = dk0 + uint64_t(ks) * kStageStep;
+          mbar_wait(&k_full[ks], kph);
+          mbar_wait(&s_free[0], jp);
           tc_fence_after();
           if (elect_one()) {
-            issue_qk(0, nstage);
+#pragma unroll
+            for (int k = 0; k < FA_D / 16; ++k)
+              umma_ss(tS0, dq0 + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk, k != 0);
             umma_commit(&s_full[0]);
           }
           __syncwarp();
+          mbar_wait(&s_free[1], jp);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < FA_D / 16; ++k)
+              umma_ss(tS1, dq1 + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk, k != 0);
+            umma_commit(&s_full[1]);
+            umma_commit(&k_empty[ks]);
+          }
+          __syncwarp();
+          if (++ks == FA_STAGES) { ks = 0; kph ^= 1; }
         }
-        mbar_wait(&p_full[1], j & 1);
+        // O_t += P_t(j) V(j)
+        const uint64_t dv = dv0 + uint64_t(vs) * kStageStep;
+        const uint32_t acc = j > 0;
+        mbar_wait(&v_full[vs], vph);
+        mbar_wait(&p_full[0], jp);
         tc_fence_after();
         if (elect_one()) {
-          issue_pv(1, stage, j > 0);
-          umma_commit(&v_empty[stage]);
-          if (more) {
-            issue_qk(1, nstage);
-            umma_commit(&s_full[1]);
-            umma_commit(&k_empty[nstage]);
-          } else {
-            umma_commit(o_full);
-          }
+#pragma unroll
+          for (int k = 0; k < FA_BN / 16; ++k)
+            umma_ts(tO0, tP0 + k * 8, dv + uint64_t(128 * k), idesc_pv, acc | (k != 0));
+          umma_commit(&pv_done[0]);
         }
         __syncwarp();
-        stage = nstage;
-        phase = nphase;
+        mbar_wait(&p_full[1], jp);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < FA_BN / 16; ++k)
+            umma_ts(tO1, tP1 + k * 8, dv + uint64_t(128 * k), idesc_pv, acc | (k != 0));
+          umma_commit(&pv_done[1]);
+          umma_commit(&v_empty[vs]);
+        }
+        __syncwarp();
+        if (++vs == FA_STAGES) { vs = 0; vph ^= 1; }
       }
     }
   } else {
@@ -223,10 +301,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const int q = warp & 3;          // TMEM lane quarter
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const uint32_t tS = tmem_base + kColS + t * 128 + lane_off;
+    const uint32_t tP = tmem_base + kColP + t * 64 + lane_off;
     const uint32_t tO = tmem_base + kColO + t * 64 + lane_off;
-    const uint32_t tL = tmem_base + kColL + t * 16 + lane_off;
     const float c = p.scale_log2;
     float m = -INFINITY;
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;   // row-sum accumulators (two packed f32x2)
+    // The two softmax warps of one SM sub-partition (tile 0 / tile 1, same lane quarter) share its MUFU pipe.  Started
+    // together they stay in lock-step (both loading and reducing, then both queueing on MUFU: 69 % XU utilisation
+    // measured).  Tile 1 therefore starts half an iteration late; nothing re-synchronises the two afterwards, so
+    // one warp's exponentials overlap the other's TMEM load / max / hand-off.
+    if (t == 1 && p.skew_cycles > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.skew_cycles) {}
+    }
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
@@ -236,6 +323,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       tmem_ld_x32(tS + 64, s + 64);
       tmem_ld_x32(tS + 96, s + 96);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);   // the tensor pipe may start S_t(j+1) now
       const int valid = p.seq - j * FA_BN;
       if (valid < FA_BN) {
 #pragma unroll
@@ -256,50 +346,68 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       } else {
         const bool grow = (mt - m) * c > 8.0f;
         if (__any_sync(0xffffffffu, grow)) {
+          // O_t may only be touched once P(j-1) V(j-1) has landed (issued a whole softmax ago)
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
           const float mn = fmaxf(m, mt);
           const float alpha = ex2((m - mn) * c);
           m = mn;
           uint32_t o[64];
           tmem_ld_x32(tO, o);
           tmem_ld_x32(tO + 32, o + 32);
-          uint32_t lsum;
-          tmem_ld_x1(tL, &lsum);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 64; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          lsum = __float_as_uint(__uint_as_float(lsum) * alpha);
           tmem_st_x32(tO, o);
           tmem_st_x32(tO + 32, o + 32);
-          tmem_st_x1(tL, lsum);
+          l0 *= alpha;
+          l1 *= alpha;
+          l2 *= alpha;
+          l3 *= alpha;
         }
       }
       const float nmc = -m * c;
       uint32_t pk[64];
 #pragma unroll
-      for (int i = 0; i < 128; i += 2) {
-        float t0, t1;
-        fma2(t0, t1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, nmc);
-        pk[i / 2] = pack_bf16x2(ex2(t0), ex2(t1));
+      for (int i = 0; i < 128; i += 4) {
+        float a0, a1, a2, a3;
+        fma2(a0, a1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, nmc);
+        fma2(a2, a3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), c, nmc);
+        if ((i & 15) < POLY16) {   // compile-time after unrolling
+          ex2_poly2(a0, a1, a0, a1);
+          ex2_poly2(a2, a3, a2, a3);
+        } else {
+          a0 = ex2(a0);
+          a1 = ex2(a1);
+          a2 = ex2(a2);
+          a3 = ex2(a3);
+        }
+        add2(l0, l1, a0, a1);
+        add2(l2, l3, a2, a3);
+        pk[i / 2] = pack_bf16x2(a0, a1);
+        pk[i / 2 + 1] = pack_bf16x2(a2, a3);
       }
-      tmem_st_x32(tS, pk);
-      tmem_st_x32(tS + 32, pk + 32);
+      if (j > 0) {   // P_t(j-1) must have been consumed by O_t += P_t(j-1) V(j-1) before it is overwritten
+        mbar_wait(&pv_done[t], (j - 1) & 1);
+        tc_fence_after();
+      }
+      tmem_st_x32(tP, pk);
+      tmem_st_x32(tP + 32, pk + 32);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[t]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
     }
     // ---- epilogue: O / l -> bf16 -> global
-    mbar_wait(o_full, 0);
+    mbar_wait(&pv_done[t], (n_kv - 1) & 1);
     tc_fence_after();
     uint32_t o[64];
     tmem_ld_x32(tO, o);
     tmem_ld_x32(tO + 32, o + 32);
     tmem_ld_wait();
-    uint32_t lbits;
-    tmem_ld_x1(tL, &lbits);
-    tmem_ld_wait();
     const int qrow = q0 + t * FA_BM + q * 32 + lane;
     if (qrow < p.seq) {
-      const float inv = 1.0f / __uint_as_float(lbits);
+      const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
       uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row_base + qrow) * p.ldo + col);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -321,6 +429,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   }
 }
 
+using FaKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FaArgs);
+
+// BYA_FA_POLY16 (0, 4, 8, 12: exponentials per 16 moved from MUFU to the FMA pipe) is a tuning knob read once.
+static FaKernel fa_pick_kernel() {
+  int poly = 4;
+  if (const char* e = std::getenv("BYA_FA_POLY16")) poly = std::atoi(e);
+  switch (poly) {
+    case 0: return fa_fwd_kernel<0>;
+    case 8: return fa_fwd_kernel<8>;
+    case 12: return fa_fwd_kernel<12>;
+    default: return fa_fwd_kernel<4>;
+  }
+}
+
 }  // namespace bya
 
 extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo,
@@ -336,11 +458,12 @@ extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, con
   if (rc) return rc;
   rc = bya_host::encode_tmap_bf16(&tv, v, uint64_t(heads) * FA_D, rows, uint64_t(ld) * 2, FA_D, FA_BN);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess)
+  static FaKernel kern = nullptr;
+  if (!kern) {
+    FaKernel kk = fa_pick_kernel();
+    if (cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess)
       return BYA_ERR_CUDA;
-    attr_set = true;
+    kern = kk;
   }
   FaArgs a;
   a.seq = seq;
@@ -348,8 +471,14 @@ extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, con
   a.batch = batch;
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
+  static int skew = -1;
+  if (skew < 0) {
+    const char* e = std::getenv("BYA_FA_SKEW");
+    skew = e ? std::atoi(e) : 1000;
+  }
+  a.skew_cycles = skew;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   dim3 grid((seq + 2 * FA_BM - 1) / (2 * FA_BM), heads, batch);
-  fa_fwd_kernel<<<grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+  kern<<<grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }
