@@ -57,13 +57,13 @@ BYA_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a watchdog: a lost arrive must not hang the GPU (a hung box is a strike).  ~2^28 polls, then trap.
+// Spin with a watchdog: a lost arrive must not hang the GPU (a hung box is a strike).  ~2^25 polls (a second or two), then trap.
 // The trap is inline on purpose: a printf/call here makes ptxas spill every live register of the caller's loop
 // (measured: 3.6 KB of stack in the attention kernel).  Build with -DBYA_DEBUG_TIMEOUT to get the message.
 BYA_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == 0x10000000u) {
+    if (++spins == 0x2000000u) {
 #ifdef BYA_DEBUG_TIMEOUT
       printf("bya: mbarrier timeout block (%d,%d,%d) thread %d smem bar 0x%x parity %u\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, smem_u32(bar), parity);

@@ -33,9 +33,10 @@ constexpr int FA_D = 64;
 constexpr int FA_BM = 128;         // query rows per tile (2 tiles per CTA)
 constexpr int FA_BN = 128;         // keys per KV tile
 constexpr int FA_STAGES = 4;       // K ring depth == V ring depth
-constexpr int FA_THREADS = 384;
 constexpr int FA_TILE_BYTES = FA_BM * FA_D * 2;  // 16 KB
-constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + 512 + 1024;
+constexpr int FA_XCH_BYTES = 3 * 2 * 2 * 128 * 4;   // [2 buffers of row max + 1 of row sums][tile][half][row] fp32
+constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + FA_XCH_BYTES + 512 + 1024;
+constexpr int fa_threads(int split) { return 128 + 256 * split; }
 
 struct FaArgs {
   int seq;        // rows per batch element (queries == keys)
@@ -43,7 +44,6 @@ struct FaArgs {
   int batch;
   int ldo;        // row stride of O in elements
   float scale_log2;  // softmax scale * log2(e)
-  int skew_cycles;   // start delay of the tile-1 softmax warps (see the kernel)
   __nv_bfloat16* out;
 };
 
@@ -128,8 +128,9 @@ BYA_DEVICE void ex2_poly2(float& y0, float& y1, float x0, float x1) {
   y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-template <int POLY16>   // POLY16: exponentials per group of 16 evaluated by ex2_poly2 (0,4,8,12)
-__global__ void __launch_bounds__(FA_THREADS, 1)
+// POLY16: exponentials per group of 16 evaluated by ex2_poly2 (0,4,8,12).  SPLIT: threads per query row (1 or 2).
+template <int POLY16, int SPLIT>
+__global__ void __launch_bounds__(fa_threads(SPLIT), 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const __grid_constant__ CUtensorMap tmap_v, const FaArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -137,7 +138,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint8_t* sQ = smem;                                   // [2][16 KB]
   uint8_t* sK = sQ + 2 * FA_TILE_BYTES;                 // [STAGES][16 KB]
   uint8_t* sV = sK + FA_STAGES * FA_TILE_BYTES;         // [STAGES][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_TILE_BYTES);
+  float* xch = reinterpret_cast<float*>(sV + FA_STAGES * FA_TILE_BYTES);   // softmax pair exchange (SPLIT == 2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_TILE_BYTES + FA_XCH_BYTES);
   uint64_t* q_full = bars;                    // [1]
   uint64_t* k_full = q_full + 1;              // [STAGES]
   uint64_t* k_empty = k_full + FA_STAGES;     // [STAGES]
@@ -172,8 +174,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 4);    // one arrive per softmax warp
-      mbar_init(&p_full[t], 4);
+      mbar_init(&s_free[t], 4 * SPLIT);    // one arrive per softmax warp
+      mbar_init(&p_full[t], 4 * SPLIT);
       mbar_init(&pv_done[t], 1);
     }
     fence_barrier_init();
@@ -186,7 +188,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
 
   if (warp < 4) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<(SPLIT == 1 ? 56 : 40)>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer (one elected thread)
       if (elect_one()) {
@@ -295,71 +297,80 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax warpgroups
-    setmaxnreg_inc<224>();
-    const int t = (warp - 4) >> 2;   // query tile 0 / 1
-    const int q = warp & 3;          // TMEM lane quarter
+    // ------------------------------------------------------------------ softmax warps
+    // SPLIT == 1: one thread per query row holds all 128 scores of a KV tile (8 warps, 224 registers).
+    // SPLIT == 2: two threads per row, 64 scores each (16 warps, 104 registers): twice the warps per SM sub-partition
+    //   to fill the issue slots a single warp leaves empty (ptxas puts an 8-cycle stall after every other MUFU.EX2; with
+    //   2 warps per sub-partition issue utilisation was 53 %).  The pair exchanges its half-row maxima through shared
+    //   memory + a 64-thread named barrier, so both use the same running max; each rescales / writes half of O.
+    setmaxnreg_inc<(SPLIT == 1 ? 224 : 104)>();   // 640 x 96 launch pool: 4x32x40 + 16x32x104 <= 61440
+    constexpr int NC = FA_BN / SPLIT;          // score columns per thread
+    constexpr int OC = FA_D / SPLIT;           // O columns per thread (rescale + final write)
+    const int sw = warp - 4;
+    const int t = sw / (4 * SPLIT);            // query tile 0 / 1
+    const int h = (sw >> 2) % SPLIT;           // which half of the row
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int row = q * 32 + lane;             // row within the tile
     const uint32_t lane_off = uint32_t(q * 32) << 16;
-    const uint32_t tS = tmem_base + kColS + t * 128 + lane_off;
-    const uint32_t tP = tmem_base + kColP + t * 64 + lane_off;
-    const uint32_t tO = tmem_base + kColO + t * 64 + lane_off;
+    const uint32_t tS = tmem_base + kColS + t * 128 + h * NC + lane_off;
+    const uint32_t tP = tmem_base + kColP + t * 64 + h * (NC / 2) + lane_off;
+    const uint32_t tO = tmem_base + kColO + t * 64 + h * OC + lane_off;
+    float* xmine = xch + (t * 2 + h) * 128 + row;          // + buf * 512
+    float* xpeer = xch + (t * 2 + (h ^ 1)) * 128 + row;
+    const int pair_bar = 1 + t * 4 + q;
     const float c = p.scale_log2;
     float m = -INFINITY;
     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;   // row-sum accumulators (two packed f32x2)
-    // The two softmax warps of one SM sub-partition (tile 0 / tile 1, same lane quarter) share its MUFU pipe.  Started
-    // together they stay in lock-step (both loading and reducing, then both queueing on MUFU: 69 % XU utilisation
-    // measured).  Tile 1 therefore starts half an iteration late; nothing re-synchronises the two afterwards, so
-    // one warp's exponentials overlap the other's TMEM load / max / hand-off.
-    if (t == 1 && p.skew_cycles > 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < p.skew_cycles) {}
-    }
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      uint32_t s[128];
-      tmem_ld_x32(tS, s);
-      tmem_ld_x32(tS + 32, s + 32);
-      tmem_ld_x32(tS + 64, s + 64);
-      tmem_ld_x32(tS + 96, s + 96);
+      uint32_t s[NC];
+#pragma unroll
+      for (int i = 0; i < NC; i += 32) tmem_ld_x32(tS + i, s + i);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[t]);   // the tensor pipe may start S_t(j+1) now
-      const int valid = p.seq - j * FA_BN;
-      if (valid < FA_BN) {
+      const int valid = p.seq - j * FA_BN - h * NC;
+      if (valid < NC) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < NC; ++i)
           if (i >= valid) s[i] = 0xff800000u;  // -inf
       }
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 128; i += 8) {
+      for (int i = 0; i < NC; i += 8) {
         mx[0] = max3(mx[0], __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
         mx[1] = max3(mx[1], __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
         mx[2] = max3(mx[2], __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
         mx[3] = max3(mx[3], __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
       }
-      const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      if (SPLIT == 2) {
+        const int buf = (j & 1) * 512;
+        xmine[buf] = mt;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mt = fmaxf(mt, xpeer[buf]);
+      }
       if (j == 0) {
         m = mt;
       } else {
         const bool grow = (mt - m) * c > 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {
+        if (__any_sync(0xffffffffu, grow)) {   // same rows, same (m, mt) in both warps of a pair: same decision
           // O_t may only be touched once P(j-1) V(j-1) has landed (issued a whole softmax ago)
           mbar_wait(&pv_done[t], (j - 1) & 1);
           tc_fence_after();
           const float mn = fmaxf(m, mt);
           const float alpha = ex2((m - mn) * c);
           m = mn;
-          uint32_t o[64];
-          tmem_ld_x32(tO, o);
-          tmem_ld_x32(tO + 32, o + 32);
+          uint32_t o[OC];
+#pragma unroll
+          for (int i = 0; i < OC; i += 32) tmem_ld_x32(tO + i, o + i);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 64; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_x32(tO, o);
-          tmem_st_x32(tO + 32, o + 32);
+          for (int i = 0; i < OC; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+#pragma unroll
+          for (int i = 0; i < OC; i += 32) tmem_st_x32(tO + i, o + i);
           l0 *= alpha;
           l1 *= alpha;
           l2 *= alpha;
@@ -367,9 +378,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
       }
       const float nmc = -m * c;
-      uint32_t pk[64];
+      uint32_t pk[NC / 2];
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < NC; i += 4) {
         float a0, a1, a2, a3;
         fma2(a0, a1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, nmc);
         fma2(a2, a3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), c, nmc);
@@ -391,26 +402,32 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         mbar_wait(&pv_done[t], (j - 1) & 1);
         tc_fence_after();
       }
-      tmem_st_x32(tP, pk);
-      tmem_st_x32(tP + 32, pk + 32);
+#pragma unroll
+      for (int i = 0; i < NC / 2; i += 32) tmem_st_x32(tP + i, pk + i);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
     }
     // ---- epilogue: O / l -> bf16 -> global
+    float l = (l0 + l1) + (l2 + l3);
+    if (SPLIT == 2) {
+      xmine[1024] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      l += xpeer[1024];
+    }
     mbar_wait(&pv_done[t], (n_kv - 1) & 1);
     tc_fence_after();
-    uint32_t o[64];
-    tmem_ld_x32(tO, o);
-    tmem_ld_x32(tO + 32, o + 32);
-    tmem_ld_wait();
-    const int qrow = q0 + t * FA_BM + q * 32 + lane;
-    if (qrow < p.seq) {
-      const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
-      uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row_base + qrow) * p.ldo + col);
+    uint32_t o[OC];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < OC; i += 32) tmem_ld_x32(tO + i, o + i);
+    tmem_ld_wait();
+    const int qrow = q0 + t * FA_BM + row;
+    if (qrow < p.seq) {
+      const float inv = 1.0f / l;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row_base + qrow) * p.ldo + col + h * OC);
+#pragma unroll
+      for (int i = 0; i < OC / 8; ++i) {
         uint4 v;
         v.x = pack_bf16x2(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
         v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
@@ -431,15 +448,26 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
 using FaKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FaArgs);
 
-// BYA_FA_POLY16 (0, 4, 8, 12: exponentials per 16 moved from MUFU to the FMA pipe) is a tuning knob read once.
-static FaKernel fa_pick_kernel() {
-  int poly = 4;
+// Tuning knobs, read once: BYA_FA_POLY16 (0, 4, 8, 12: exponentials per 16 moved from MUFU to the FMA pipe) and
+// BYA_FA_SPLIT (1 or 2 threads per query row).
+static FaKernel fa_pick_kernel(int* threads) {
+  int poly = 4, split = 1;
   if (const char* e = std::getenv("BYA_FA_POLY16")) poly = std::atoi(e);
+  if (const char* e = std::getenv("BYA_FA_SPLIT")) split = std::atoi(e) == 1 ? 1 : 2;
+  *threads = fa_threads(split);
+  if (split == 1) {
+    switch (poly) {
+      case 0: return fa_fwd_kernel<0, 1>;
+      case 8: return fa_fwd_kernel<8, 1>;
+      case 12: return fa_fwd_kernel<12, 1>;
+      default: return fa_fwd_kernel<4, 1>;
+    }
+  }
   switch (poly) {
-    case 0: return fa_fwd_kernel<0>;
-    case 8: return fa_fwd_kernel<8>;
-    case 12: return fa_fwd_kernel<12>;
-    default: return fa_fwd_kernel<4>;
+    case 0: return fa_fwd_kernel<0, 2>;
+    case 8: return fa_fwd_kernel<8, 2>;
+    case 12: return fa_fwd_kernel<12, 2>;
+    default: return fa_fwd_kernel<4, 2>;
   }
 }
 
@@ -459,8 +487,9 @@ extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, con
   rc = bya_host::encode_tmap_bf16(&tv, v, uint64_t(heads) * FA_D, rows, uint64_t(ld) * 2, FA_D, FA_BN);
   if (rc) return rc;
   static FaKernel kern = nullptr;
+  static int threads = 0;
   if (!kern) {
-    FaKernel kk = fa_pick_kernel();
+    FaKernel kk = fa_pick_kernel(&threads);
     if (cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess)
       return BYA_ERR_CUDA;
     kern = kk;
@@ -471,14 +500,8 @@ extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, con
   a.batch = batch;
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
-  static int skew = -1;
-  if (skew < 0) {
-    const char* e = std::getenv("BYA_FA_SKEW");
-    skew = e ? std::atoi(e) : 1000;
-  }
-  a.skew_cycles = skew;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   dim3 grid((seq + 2 * FA_BM - 1) / (2 * FA_BM), heads, batch);
-  kern<<<grid, FA_THREADS, FA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+  kern<<<grid, threads, FA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }
