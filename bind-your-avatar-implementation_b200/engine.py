@@ -80,6 +80,15 @@ class _Workspace:
         return t
 
 
+def _tree_values(x):
+    """Nested dict / list of tensors -> nested lists in a deterministic order."""
+    if isinstance(x, dict):
+        return [_tree_values(x[k]) for k in sorted(x)]
+    if isinstance(x, (list, tuple)):
+        return [_tree_values(y) for y in x]
+    return x
+
+
 def run_router(rp: RouterPack, ws: _Workspace, qf: torch.Tensor, kmat: torch.Tensor, layer: int, chars: int, frames: int,
                hw: int, out: torch.Tensor) -> torch.Tensor:
     """qf [Nv,2048] (natural head-major face queries) , kmat [C*512,2048] -> out [Nv,C] fp32 soft routing.
@@ -156,6 +165,7 @@ class StepEngine:
         self._pack()
         self._prologue_key = None
         self._prologue = None
+        self._graphs: Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------------------------------------ packing
     def _pack(self):
@@ -272,11 +282,79 @@ class StepEngine:
             L_["w_qkv_sp"] = qkv_rows_by_destination(L_["w_qkv"], self.D, P)
             L_["b_qkv_sp"] = qkv_rows_by_destination(L_["b_qkv"], self.D, P)
 
+    @staticmethod
+    def _prologue_cache_key(id_cond, id_vit_hidden, audio_embeds, frames, use_router):
+        """Identity of the timestep-invariant inputs (the pipeline passes the same tensors on all 50 steps)."""
+        ts = list(id_cond) + [v for l in id_vit_hidden for v in l] + ([audio_embeds] if audio_embeds is not None else [])
+        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts) + (frames, use_router)
+
+    # ------------------------------------------------------------------------------------------------ CUDA-graph replay
+    @torch.no_grad()
+    def step_graphed(self, hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,
+                     audio_embeds, af_matrix, routing_logits_forcing=None, per_frame_forcing=False, cache_prologue=True):
+        """`step()` captured once per input geometry into a CUDA graph and replayed: the ~2 000 kernel launches of a
+        step cost ~0.4 s of host time through ctypes, which bounds the step as soon as the kernels take less.  Inputs
+        are copied into the graph's static buffers (device or pinned-host sources, asynchronously on the current
+        stream); the returned tensor is the graph's static output (valid until the next call)."""
+        dev = self.device
+        nested = dict(hidden_states=hidden_states, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
+                      image_rotary_emb=list(image_rotary_emb), id_cond=list(id_cond),
+                      id_vit_hidden=[list(l) for l in id_vit_hidden], audio_embeds=audio_embeds, af_matrix=af_matrix,
+                      routing_logits_forcing=routing_logits_forcing)
+
+        def flat(x):
+            if isinstance(x, (list, tuple)):
+                return [t for y in x for t in flat(y)]
+            return [x]
+
+        def like(x):
+            if isinstance(x, (list, tuple)):
+                return [like(y) for y in x]
+            return None if x is None else x.detach().to(dev, copy=True)
+
+        sig = tuple(None if t is None else (tuple(t.shape), t.dtype) for t in flat(list(nested.values())))
+        sig += (per_frame_forcing, cache_prologue)
+        Fr = hidden_states.shape[1]
+        use_router = routing_logits_forcing is None
+        key = self._prologue_cache_key(id_cond, id_vit_hidden, audio_embeds, Fr, use_router) if cache_prologue else None
+        g = self._graphs.get(sig)
+        if g is None:
+            static = {k: like(v) for k, v in nested.items()}
+            kw = dict(static, image_rotary_emb=tuple(static["image_rotary_emb"]), per_frame_forcing=per_frame_forcing,
+                      cache_prologue=False)
+            if cache_prologue:   # the prologue stays outside the graph: it is recomputed only when its inputs change
+                kw["_pro"] = self.prologue(static["id_cond"], static["id_vit_hidden"], static["audio_embeds"], Fr, use_router)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up outside capture: workspaces, tensor maps, lazy module state
+                self.step(**kw)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            l0 = ops.LAUNCHES
+            with torch.cuda.graph(graph):
+                out = self.step(**kw)
+            g = dict(graph=graph, static=static, out=out, launches=ops.LAUNCHES - l0, pro=kw.get("_pro"), pro_key=key)
+            self._graphs[sig] = g
+        else:
+            for dst, src in zip(flat(list(g["static"].values())), flat(list(nested.values()))):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            if cache_prologue and key != g["pro_key"]:
+                new = self.prologue(g["static"]["id_cond"], g["static"]["id_vit_hidden"], g["static"]["audio_embeds"], Fr,
+                                    use_router)
+                for dst, src in zip(flat(_tree_values(g["pro"])), flat(_tree_values(new))):
+                    if dst is not None:
+                        dst.copy_(src)
+                g["pro_key"] = key
+        g["graph"].replay()
+        ops.LAUNCHES += g["launches"]
+        return g["out"]
+
     # ------------------------------------------------------------------------------------------------ one step
     @torch.no_grad()
     def step(self, hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,
              audio_embeds, af_matrix, routing_logits_forcing=None, per_frame_forcing=False, cache_prologue=True,
-             taps: Optional[dict] = None):
+             taps: Optional[dict] = None, _pro: Optional[dict] = None):
         m, cfg, D, ws = self.model, self.model.config, self.D, self.ws
         dev, bf = self.device, torch.bfloat16
         B, Fr, Cin, Hl, Wl = hidden_states.shape
@@ -311,14 +389,14 @@ class StepEngine:
                 self.router = RouterPack(m.router)
 
         # ---- prologue (cached per generation)
-        key = None
-        if cache_prologue:
-            ts = list(id_cond) + [v for l in id_vit_hidden for v in l] + ([audio_embeds] if audio_embeds is not None else [])
-            key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts) + (Fr, use_router)
-        if key is None or key != self._prologue_key:
-            self._prologue = self.prologue(id_cond, id_vit_hidden, audio_embeds, Fr, use_router)
-            self._prologue_key = key
-        pro = self._prologue
+        if _pro is not None:
+            pro = _pro
+        else:
+            key = self._prologue_cache_key(id_cond, id_vit_hidden, audio_embeds, Fr, use_router) if cache_prologue else None
+            if key is None or key != self._prologue_key:
+                self._prologue = self.prologue(id_cond, id_vit_hidden, audio_embeds, Fr, use_router)
+                self._prologue_key = key
+            pro = self._prologue
         if tap:
             tap("face_tokens", pro["face_tokens"])
             if has_audio:

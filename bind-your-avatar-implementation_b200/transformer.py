@@ -130,6 +130,7 @@ class BindyouravatarTransformer3DModel(nn.Module):
         self._engine_sig = None
         self._processors: Dict[str, Any] = {}
         self.cache_prologue = True
+        self.use_cuda_graph = False  # replay the step as one CUDA graph per input geometry (engine.step_graphed)
         self._sp_group = None  # set by bya_b200.sp.enable(): Ulysses sequence parallelism over this process group
 
     # ------------------------------------------------------------------ reference surface: config / device / dtype
@@ -285,6 +286,12 @@ class BindyouravatarTransformer3DModel(nn.Module):
         eng = self.engine()
         if denoise_step == 0:
             eng._prologue_key = None  # a new generation: recompute the timestep-invariant prologue
+        if self.use_cuda_graph and taps is None and self._sp_group is None:
+            out = eng.step_graphed(hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,
+                                   audio_embeds if self.is_train_audio else None, af_matrix,
+                                   routing_logits_forcing=routing_logits_forcing, per_frame_forcing=per_frame_forcing,
+                                   cache_prologue=self.cache_prologue)
+            return (out, None, None, None, None)
         out = eng.step(hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,
                        audio_embeds if self.is_train_audio else None, af_matrix,
                        routing_logits_forcing=routing_logits_forcing, per_frame_forcing=per_frame_forcing,

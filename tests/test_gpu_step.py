@@ -172,3 +172,28 @@ def test_module_level_interfaces(c1):
     assert cos(a, a_ref) >= 0.999
     with pytest.raises(AssertionError):
         m.audio_model.sliding_windows(torch.zeros(1, 50, 12, 768), cfg.frames)  # audio_model.py:190
+
+
+def test_cuda_graph_replay_equals_eager(c1):
+    """`use_cuda_graph`: the captured step replays bit-identically to the eager step, picks up new inputs (copied
+    into the graph's static buffers, here from pinned host memory) and recomputes the cached prologue when the
+    timestep-invariant inputs change."""
+    from bya_b200.synth import make_inputs
+
+    cfg, m, _ = c1
+    a = make_inputs(cfg, 1234, device="cuda", dtype=torch.bfloat16)
+    b = make_inputs(cfg, 99, device="cuda", dtype=torch.bfloat16)
+    eager = [m(**x)[0].clone() for x in (a, b)]
+    m.use_cuda_graph = True
+    try:
+        g0 = m(**a)[0].clone()              # capture
+        g1 = m(**b)[0].clone()              # replay: every input (incl. the prologue inputs) changed
+        host = dict(b)
+        host["hidden_states"] = b["hidden_states"].cpu().pin_memory()
+        g2 = m(**host)[0].clone()           # replay from a pinned-host source
+        g3 = m(**a)[0].clone()
+    finally:
+        m.use_cuda_graph = False
+        m.engine()._graphs.clear()
+    assert torch.equal(g0, eager[0]) and torch.equal(g3, eager[0])
+    assert torch.equal(g1, eager[1]) and torch.equal(g2, eager[1])
