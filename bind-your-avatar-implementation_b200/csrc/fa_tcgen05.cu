@@ -6,26 +6,36 @@
 // [rows, ld] with head h at columns h*64.. — so no head-major copy is ever made.
 //
 // One CTA = one (batch, head, 256 query rows) = two 128-row query tiles; KV tiles of 128 keys.  Warp roles:
-//   warp 0       TMA producer (one thread): Q once, then 4-deep rings of K and V tiles
-//   warp 1       MMA issuer (one thread):   S_t = Q_t K^T (tcgen05.mma SS, fp32 in TMEM),
+//   warps 0-3    softmax for query tile 0   (one thread per query row; tcgen05.ld S -> exp2 -> tcgen05.st P)
+//   warps 4-7    softmax for query tile 1
+//   warp 8       TMA producer (one thread): Q once, then 4-deep rings of K and V tiles
+//   warp 9       MMA issuer (one thread):   S_t = Q_t K^T (tcgen05.mma SS, fp32 in TMEM),
 //                                           O_t += P_t V  (tcgen05.mma TS: P read from TMEM, V consumed MN-major
 //                                           straight from its natural [key, d] layout)
-//   warp 2       TMEM allocator
-//   warps 4-7    softmax for query tile 0   (one thread per query row; tcgen05.ld S -> exp2 -> tcgen05.st P)
-//   warps 8-11   softmax for query tile 1
+//   warp 10      TMEM allocator
+// The issuing warps carry the HIGHEST warp ids on purpose: the sub-partition arbiter prefers higher ids, and a
+// starved MMA issuer (it shares a sub-partition with two softmax warps) was the critical path of the whole kernel
+// (clock64 timeline: ~2000 cycles per KV tile spent in its ~270-instruction loop).
 // TMEM (512 columns): S_t [128t, 128t+128)   P_t [256+64t, +64) (packed bf16)   O_t [384+64t, +64).
 // S and P live in DIFFERENT columns, so the softmax warps hand S back (`s_free`) as soon as the scores are in
 // registers and Q K^T of KV tile j+1 runs on the tensor pipe while the exponentials of tile j are being computed:
-// in steady state neither side waits for the other (the round-1 profile had the softmax warps waiting on `s_full`
-// for 29 % of their time and the single MMA warp spending 2/3 of its time on loop overhead).
-// d=64 attention is exp-bound (16 ex2/clk/SM vs 8192 MMA-FLOP/clk/SM): FA_POLY16 of every 16 exponentials are
-// evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel. error 8.8e-5, far below the
-// bf16 rounding of P) instead of MUFU.EX2.  Row sums are accumulated in registers with packed f32x2 adds; the
-// running max uses lazy rescaling (O in TMEM is only rescaled when the max grows by more than 2^8).
+// in steady state neither side waits for the other.
+// d=64 attention is exp-bound (MUFU.EX2: 8 cycles per warp instruction, measured; the MMAs of the same scores take
+// 4): POLY16 of every 16 exponentials are evaluated on the FMA pipe instead (Cody-Waite split + degree-3 minimax
+// polynomial, max rel. error 8.8e-5, far below the bf16 rounding of P).  Row sums are accumulated in registers.
+// Two softmax variants:
+//   general  (bya_attention_d64):         running max with lazy rescaling (O in TMEM is only rescaled when the max
+//                                         grows by more than 2^8); the whole 128-score row is held in registers.
+//   bounded  (bya_attention_d64_bounded): the caller guarantees |q.k| <= bound (log2 units, bound <= 64) — true for the
+//                                         joint self-attention, whose q and k are LayerNorm-ed per head (|q|,|k| <=
+//                                         8 max|gamma| + |beta|) — so softmax(s) = 2^s / sum 2^s needs no max, no
+//                                         subtraction and no rescaling: the scores go straight from the TMEM
+//                                         load into the exponentials.
 #include "common.cuh"
 #include "../../include/bya.h"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace bya {
 
@@ -34,9 +44,8 @@ constexpr int FA_BM = 128;         // query rows per tile (2 tiles per CTA)
 constexpr int FA_BN = 128;         // keys per KV tile
 constexpr int FA_STAGES = 4;       // K ring depth == V ring depth
 constexpr int FA_TILE_BYTES = FA_BM * FA_D * 2;  // 16 KB
-constexpr int FA_XCH_BYTES = 3 * 2 * 2 * 128 * 4;   // [2 buffers of row max + 1 of row sums][tile][half][row] fp32
-constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + FA_XCH_BYTES + 512 + 1024;
-constexpr int fa_threads(int split) { return 128 + 256 * split; }
+constexpr int fa_threads(int nt) { return 256 * nt + 128; }   // nt softmax threads per query row + one issuing warpgroup
+constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + 512 + 1024;
 
 struct FaArgs {
   int seq;        // rows per batch element (queries == keys)
@@ -45,7 +54,15 @@ struct FaArgs {
   int ldo;        // row stride of O in elements
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* out;
+  long long* trace;   // debug (BYA_FA_TRACE): [32 iterations][16 events] clock64 stamps of CTA (0,0,0), else NULL
 };
+
+// debug timeline: event e of iteration j (only CTA 0, only while j < 32)
+#define FA_TRACE(e, j)                                                                              \
+  do {                                                                                              \
+    if (p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 32 && lane == 0)  \
+      p.trace[(j) * 16 + (e)] = clock64();                                                          \
+  } while (0)
 
 template <int R>
 BYA_DEVICE void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
@@ -94,11 +111,14 @@ BYA_DEVICE float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): x = n + f, n = floor(x) via a round-down magic add,
+// 2^x for |x| < 126 on the FMA / ALU pipes (no MUFU): x = n + f, n = floor(x) via a round-down magic add,
 // 2^f ~ degree-3 minimax polynomial on [0,1), exponent patched in with one integer shift-add.
+template <bool CLAMP>   // CLAMP: inputs may be below -126 (the result then saturates at 2^-126 instead of wrapping)
 BYA_DEVICE void ex2_poly2(float& y0, float& y1, float x0, float x1) {
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
+  if (CLAMP) {
+    x0 = fmaxf(x0, -126.0f);
+    x1 = fmaxf(x1, -126.0f);
+  }
   float t0, t1, n0, n1, f0, f1, p0, p1;
   asm("{\n\t.reg .b64 va, vb;\n\t"
       "mov.b64 va, {%2, %3};\n\t"
@@ -128,9 +148,13 @@ BYA_DEVICE void ex2_poly2(float& y0, float& y1, float x0, float x1) {
   y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-// POLY16: exponentials per group of 16 evaluated by ex2_poly2 (0,4,8,12).  SPLIT: threads per query row (1 or 2).
-template <int POLY16, int SPLIT>
-__global__ void __launch_bounds__(fa_threads(SPLIT), 1)
+// POLY16: exponentials per group of 16 evaluated by ex2_poly2 (0,4,8,12).  BOUNDED: see the header.
+// NT: softmax threads per query row.  NT = 2 (bounded only: without a running max the two halves of a row share
+// nothing but the final row sum) doubles the warps per SM sub-partition.  Measured: no gain (1066 vs 1055 TFLOP/s) —
+// the exp phase is bound by dispatch/pipe occupancy (every f32x2 / F2FP instruction holds its pipe for 2 cycles), not by
+// latency hiding — so NT = 1 is the default; the variant is kept for the next round of tuning.
+template <int POLY16, bool BOUNDED, int NT>
+__global__ void __launch_bounds__(fa_threads(NT), 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const __grid_constant__ CUtensorMap tmap_v, const FaArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -138,8 +162,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint8_t* sQ = smem;                                   // [2][16 KB]
   uint8_t* sK = sQ + 2 * FA_TILE_BYTES;                 // [STAGES][16 KB]
   uint8_t* sV = sK + FA_STAGES * FA_TILE_BYTES;         // [STAGES][16 KB]
-  float* xch = reinterpret_cast<float*>(sV + FA_STAGES * FA_TILE_BYTES);   // softmax pair exchange (SPLIT == 2)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_TILE_BYTES + FA_XCH_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_TILE_BYTES);
   uint64_t* q_full = bars;                    // [1]
   uint64_t* k_full = q_full + 1;              // [STAGES]
   uint64_t* k_empty = k_full + FA_STAGES;     // [STAGES]
@@ -159,12 +182,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   const int n_kv = (p.seq + FA_BN - 1) / FA_BN;
   const int col = head * FA_D;
 
-  if (warp == 0 && lane == 0) {
+  constexpr int W0 = 8 * NT;   // first warp of the issuing warpgroup
+  if (warp == W0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == W0 + 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < FA_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
@@ -174,22 +198,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 4 * SPLIT);    // one arrive per softmax warp
-      mbar_init(&p_full[t], 4 * SPLIT);
+      mbar_init(&s_free[t], 4 * NT);    // one arrive per softmax warp
+      mbar_init(&p_full[t], 4 * NT);
       mbar_init(&pv_done[t], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == W0 + 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
 
-  if (warp < 4) {
-    setmaxnreg_dec<(SPLIT == 1 ? 56 : 40)>();
-    if (warp == 0) {
+  if (warp >= W0) {
+    setmaxnreg_dec<(NT == 1 ? 56 : 40)>();
+    if (warp == W0) {
       // ---------------------------------------------------------------- TMA producer (one elected thread)
       if (elect_one()) {
         mbar_arrive_expect_tx(q_full, 2 * FA_TILE_BYTES);
@@ -213,7 +237,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (++vs == FA_STAGES) { vs = 0; vph ^= 1; }
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == W0 + 1) {
       // ---------------------------------------------------------------- MMA issuer
       // The whole warp runs the warp-uniform loop and polls the barriers; one elected lane issues (ptxas keeps
       // descriptors in uniform registers only when control flow is provably uniform).
@@ -250,6 +274,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const uint64_t dk = dk0 + uint64_t(ks) * kStageStep;
           mbar_wait(&k_full[ks], kph);
           mbar_wait(&s_free[0], jp);
+          FA_TRACE(8, j);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
@@ -259,6 +284,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           }
           __syncwarp();
           mbar_wait(&s_free[1], jp);
+          FA_TRACE(9, j);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
@@ -275,6 +301,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const uint32_t acc = j > 0;
         mbar_wait(&v_full[vs], vph);
         mbar_wait(&p_full[0], jp);
+        FA_TRACE(10, j);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -284,6 +311,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         __syncwarp();
         mbar_wait(&p_full[1], jp);
+        FA_TRACE(11, j);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -293,128 +321,193 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           umma_commit(&v_empty[vs]);
         }
         __syncwarp();
+        FA_TRACE(12, j);
         if (++vs == FA_STAGES) { vs = 0; vph ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax warps
-    // SPLIT == 1: one thread per query row holds all 128 scores of a KV tile (8 warps, 224 registers).
-    // SPLIT == 2: two threads per row, 64 scores each (16 warps, 104 registers): twice the warps per SM sub-partition
-    //   to fill the issue slots a single warp leaves empty (ptxas puts an 8-cycle stall after every other MUFU.EX2; with
-    //   2 warps per sub-partition issue utilisation was 53 %).  The pair exchanges its half-row maxima through shared
-    //   memory + a 64-thread named barrier, so both use the same running max; each rescales / writes half of O.
-    setmaxnreg_inc<(SPLIT == 1 ? 224 : 104)>();   // 640 x 96 launch pool: 4x32x40 + 16x32x104 <= 61440
-    constexpr int NC = FA_BN / SPLIT;          // score columns per thread
-    constexpr int OC = FA_D / SPLIT;           // O columns per thread (rescale + final write)
-    const int sw = warp - 4;
-    const int t = sw / (4 * SPLIT);            // query tile 0 / 1
-    const int h = (sw >> 2) % SPLIT;           // which half of the row
-    const int q = warp & 3;                    // TMEM lane quarter
-    const int row = q * 32 + lane;             // row within the tile
+    // ------------------------------------------------------------------ softmax warps (one thread per query row)
+    static_assert(NT == 1 || BOUNDED, "two threads per row need the max-free softmax");
+    // register pool of the launch: 65536 / threads rounded down to 8 -> 168 (NT=1) / 96 (NT=2) per thread
+    setmaxnreg_inc<(NT == 1 ? 224 : 104)>();
+    constexpr int NC = FA_BN / NT;   // score columns per thread
+    constexpr int OC = FA_D / NT;    // O columns per thread (final normalisation + store)
+    const int t = (warp / (4 * NT));   // query tile 0 / 1
+    const int h = (warp >> 2) % NT;  // which part of the row
+    const int q = warp & 3;          // TMEM lane quarter
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const uint32_t tS = tmem_base + kColS + t * 128 + h * NC + lane_off;
     const uint32_t tP = tmem_base + kColP + t * 64 + h * (NC / 2) + lane_off;
     const uint32_t tO = tmem_base + kColO + t * 64 + h * OC + lane_off;
-    float* xmine = xch + (t * 2 + h) * 128 + row;          // + buf * 512
-    float* xpeer = xch + (t * 2 + (h ^ 1)) * 128 + row;
-    const int pair_bar = 1 + t * 4 + q;
-    const float c = p.scale_log2;
-    float m = -INFINITY;
     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;   // row-sum accumulators (two packed f32x2)
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      uint32_t s[NC];
+
+    if constexpr (BOUNDED) {
+      // P = 2^s, no max, no scaling: exponentiate straight off the TMEM load, P stored back in 32-key chunks.
+      auto exp_chunk = [&](const uint32_t* sc, uint32_t* pk, int col0, int valid, auto masked) {
 #pragma unroll
-      for (int i = 0; i < NC; i += 32) tmem_ld_x32(tS + i, s + i);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[t]);   // the tensor pipe may start S_t(j+1) now
-      const int valid = p.seq - j * FA_BN - h * NC;
-      if (valid < NC) {
+        for (int i = 0; i < 32; i += 4) {
+          float a0 = __uint_as_float(sc[i]), a1 = __uint_as_float(sc[i + 1]);
+          float a2 = __uint_as_float(sc[i + 2]), a3 = __uint_as_float(sc[i + 3]);
+          if (decltype(masked)::value) {   // last KV tile only: keys past the sequence end get weight 2^-100
+            a0 = (col0 + i < valid) ? a0 : -100.f;
+            a1 = (col0 + i + 1 < valid) ? a1 : -100.f;
+            a2 = (col0 + i + 2 < valid) ? a2 : -100.f;
+            a3 = (col0 + i + 3 < valid) ? a3 : -100.f;
+          }
+          if ((i & 15) < POLY16) {   // compile-time after unrolling
+            ex2_poly2<false>(a0, a1, a0, a1);
+            ex2_poly2<false>(a2, a3, a2, a3);
+          } else {
+            a0 = ex2(a0);
+            a1 = ex2(a1);
+            a2 = ex2(a2);
+            a3 = ex2(a3);
+          }
+          add2(l0, l1, a0, a1);
+          add2(l2, l3, a2, a3);
+          pk[i / 2] = pack_bf16x2(a0, a1);
+          pk[i / 2 + 1] = pack_bf16x2(a2, a3);
+        }
+      };
+      // one KV tile: S_t(j) -> P_t(j)
+      auto tile = [&](int j, int valid, auto masked) {
+        if (q == 0 && h == 0) FA_TRACE(t * 4 + 0, j);
+        uint32_t s[NC];
 #pragma unroll
-        for (int i = 0; i < NC; ++i)
-          if (i >= valid) s[i] = 0xff800000u;  // -inf
-      }
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < NC; i += 8) {
-        mx[0] = max3(mx[0], __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx[1] = max3(mx[1], __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-        mx[2] = max3(mx[2], __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-        mx[3] = max3(mx[3], __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-      }
-      float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      if (SPLIT == 2) {
-        const int buf = (j & 1) * 512;
-        xmine[buf] = mt;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        mt = fmaxf(mt, xpeer[buf]);
-      }
-      if (j == 0) {
-        m = mt;
-      } else {
-        const bool grow = (mt - m) * c > 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {   // same rows, same (m, mt) in both warps of a pair: same decision
-          // O_t may only be touched once P(j-1) V(j-1) has landed (issued a whole softmax ago)
+        for (int i = 0; i < NC; i += 32) tmem_ld_x32(tS + i, s + i);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);   // hand S_t back at once: Q K^T of tile j+1 overlaps these exps
+        if (q == 0 && h == 0) FA_TRACE(t * 4 + 1, j);
+        uint32_t pk[NC / 2];
+        exp_chunk(s, pk, 0, valid, masked);
+        if (NC > 32) exp_chunk(s + 32, pk + 16, 32, valid, masked);
+        // P_t(j-1) must have been consumed by O_t += P_t(j-1) V(j-1) before it is overwritten.  That MMA was issued
+        // when the previous iteration ended (and queues behind the other tile's): waiting here, well into this
+        // iteration, costs nothing; waiting before the first exponential stalled tile 1 for ~500 cycles per KV tile.
+        if (q == 0 && h == 0) FA_TRACE(t * 4 + 2, j);
+        if (j > 0) {
           mbar_wait(&pv_done[t], (j - 1) & 1);
           tc_fence_after();
-          const float mn = fmaxf(m, mt);
-          const float alpha = ex2((m - mn) * c);
-          m = mn;
-          uint32_t o[OC];
-#pragma unroll
-          for (int i = 0; i < OC; i += 32) tmem_ld_x32(tO + i, o + i);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < OC; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-#pragma unroll
-          for (int i = 0; i < OC; i += 32) tmem_st_x32(tO + i, o + i);
-          l0 *= alpha;
-          l1 *= alpha;
-          l2 *= alpha;
-          l3 *= alpha;
         }
-      }
-      const float nmc = -m * c;
-      uint32_t pk[NC / 2];
-#pragma unroll
-      for (int i = 0; i < NC; i += 4) {
-        float a0, a1, a2, a3;
-        fma2(a0, a1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, nmc);
-        fma2(a2, a3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), c, nmc);
-        if ((i & 15) < POLY16) {   // compile-time after unrolling
-          ex2_poly2(a0, a1, a0, a1);
-          ex2_poly2(a2, a3, a2, a3);
-        } else {
-          a0 = ex2(a0);
-          a1 = ex2(a1);
-          a2 = ex2(a2);
-          a3 = ex2(a3);
+        if (q == 0 && h == 0) FA_TRACE(t * 4 + 3, j);
+        if (NC > 32) tmem_st_x32(tP, pk);
+        else tmem_st_x16(tP, pk);
+        if (NC > 64) {
+          exp_chunk(s + 64, pk + 32, 64, valid, masked);
+          tmem_st_x16(tP + 32, pk + 32);
+          exp_chunk(s + 96, pk + 48, 96, valid, masked);
+          tmem_st_x16(tP + 48, pk + 48);
         }
-        add2(l0, l1, a0, a1);
-        add2(l2, l3, a2, a3);
-        pk[i / 2] = pack_bf16x2(a0, a1);
-        pk[i / 2 + 1] = pack_bf16x2(a2, a3);
-      }
-      if (j > 0) {   // P_t(j-1) must have been consumed by O_t += P_t(j-1) V(j-1) before it is overwritten
-        mbar_wait(&pv_done[t], (j - 1) & 1);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      };
+      for (int j = 0; j < n_kv; ++j) {
+        const int valid = p.seq - j * FA_BN - h * NC;   // valid keys among this thread's NC columns
+        mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
+        if (valid >= NC) tile(j, valid, std::false_type{});
+        else tile(j, valid, std::true_type{});
       }
+    } else {
+      const float c = p.scale_log2;
+      float m = -INFINITY;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t s[128];
+        tmem_ld_x32(tS, s);
+        tmem_ld_x32(tS + 32, s + 32);
+        tmem_ld_x32(tS + 64, s + 64);
+        tmem_ld_x32(tS + 96, s + 96);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);   // the tensor pipe may start S_t(j+1) now
+        const int valid = p.seq - j * FA_BN;
+        if (valid < FA_BN) {
 #pragma unroll
-      for (int i = 0; i < NC / 2; i += 32) tmem_st_x32(tP + i, pk + i);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
+          for (int i = 0; i < 128; ++i)
+            if (i >= valid) s[i] = 0xff800000u;  // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 128; i += 8) {
+          mx[0] = max3(mx[0], __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+          mx[1] = max3(mx[1], __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+          mx[2] = max3(mx[2], __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+          mx[3] = max3(mx[3], __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+        }
+        const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if (j == 0) {
+          m = mt;
+        } else {
+          const bool grow = (mt - m) * c > 8.0f;
+          if (__any_sync(0xffffffffu, grow)) {
+            // O_t may only be touched once P(j-1) V(j-1) has landed (issued a whole softmax ago)
+            mbar_wait(&pv_done[t], (j - 1) & 1);
+            tc_fence_after();
+            const float mn = fmaxf(m, mt);
+            const float alpha = ex2((m - mn) * c);
+            m = mn;
+            uint32_t o[64];
+            tmem_ld_x32(tO, o);
+            tmem_ld_x32(tO + 32, o + 32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 64; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tO, o);
+            tmem_st_x32(tO + 32, o + 32);
+            l0 *= alpha;
+            l1 *= alpha;
+            l2 *= alpha;
+            l3 *= alpha;
+          }
+        }
+        const float nmc = -m * c;
+        uint32_t pk[64];
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          float a0, a1, a2, a3;
+          fma2(a0, a1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), c, nmc);
+          fma2(a2, a3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), c, nmc);
+          if ((i & 15) < POLY16) {   // compile-time after unrolling
+            ex2_poly2<true>(a0, a1, a0, a1);
+            ex2_poly2<true>(a2, a3, a2, a3);
+          } else {
+            a0 = ex2(a0);
+            a1 = ex2(a1);
+            a2 = ex2(a2);
+            a3 = ex2(a3);
+          }
+          add2(l0, l1, a0, a1);
+          add2(l2, l3, a2, a3);
+          pk[i / 2] = pack_bf16x2(a0, a1);
+          pk[i / 2 + 1] = pack_bf16x2(a2, a3);
+        }
+        if (j > 0) {   // P_t(j-1) must have been consumed by O_t += P_t(j-1) V(j-1) before it is overwritten
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_x32(tP, pk);
+        tmem_st_x32(tP + 32, pk + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
     }
     // ---- epilogue: O / l -> bf16 -> global
     float l = (l0 + l1) + (l2 + l3);
-    if (SPLIT == 2) {
-      xmine[1024] = l;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      l += xpeer[1024];
+    if (NT == 2) {   // the two threads of a row exchange their partial row sums through (now idle) K-ring shared memory
+      mbar_wait(&pv_done[t], (n_kv - 1) & 1);   // every MMA of this tile has completed: no tile reads sK any more
+      float* xch = reinterpret_cast<float*>(sK) + t * 256 + q * 32 + lane;   // [tile][half][row]
+      xch[h * 128] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + q) : "memory");
+      l += xch[(h ^ 1) * 128];
     }
     mbar_wait(&pv_done[t], (n_kv - 1) & 1);
     tc_fence_after();
@@ -422,7 +515,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < OC; i += 32) tmem_ld_x32(tO + i, o + i);
     tmem_ld_wait();
-    const int qrow = q0 + t * FA_BM + row;
+    const int qrow = q0 + t * FA_BM + q * 32 + lane;
     if (qrow < p.seq) {
       const float inv = 1.0f / l;
       uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row_base + qrow) * p.ldo + col + h * OC);
@@ -440,7 +533,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == W0 + 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -448,34 +541,35 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
 using FaKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FaArgs);
 
-// Tuning knobs, read once: BYA_FA_POLY16 (0, 4, 8, 12: exponentials per 16 moved from MUFU to the FMA pipe) and
-// BYA_FA_SPLIT (1 or 2 threads per query row).
+// Tuning knobs, read once: BYA_FA_POLY16 / BYA_FA_POLY16_BOUNDED (0, 4, 8, 12: exponentials per 16 moved from MUFU
+// to the FMA pipe) and BYA_FA_NT (bounded kernel only: 1 or 2 softmax threads per query row).
+template <bool BOUNDED>
 static FaKernel fa_pick_kernel(int* threads) {
-  int poly = 4, split = 1;
-  if (const char* e = std::getenv("BYA_FA_POLY16")) poly = std::atoi(e);
-  if (const char* e = std::getenv("BYA_FA_SPLIT")) split = std::atoi(e) == 1 ? 1 : 2;
-  *threads = fa_threads(split);
-  if (split == 1) {
-    switch (poly) {
-      case 0: return fa_fwd_kernel<0, 1>;
-      case 8: return fa_fwd_kernel<8, 1>;
-      case 12: return fa_fwd_kernel<12, 1>;
-      default: return fa_fwd_kernel<4, 1>;
+  int poly = 4, nt = 1;
+  if (const char* e = std::getenv(BOUNDED ? "BYA_FA_POLY16_BOUNDED" : "BYA_FA_POLY16")) poly = std::atoi(e);
+  if (const char* e = std::getenv("BYA_FA_NT")) nt = (BOUNDED && std::atoi(e) == 2) ? 2 : 1;
+  *threads = fa_threads(nt);
+  if constexpr (BOUNDED) {
+    if (nt == 2) {
+      switch (poly) {
+        case 0: return fa_fwd_kernel<0, true, 2>;
+        case 4: return fa_fwd_kernel<4, true, 2>;
+        case 12: return fa_fwd_kernel<12, true, 2>;
+        default: return fa_fwd_kernel<8, true, 2>;
+      }
     }
   }
   switch (poly) {
-    case 0: return fa_fwd_kernel<0, 2>;
-    case 8: return fa_fwd_kernel<8, 2>;
-    case 12: return fa_fwd_kernel<12, 2>;
-    default: return fa_fwd_kernel<4, 2>;
+    case 0: return fa_fwd_kernel<0, BOUNDED, 1>;
+    case 4: return fa_fwd_kernel<4, BOUNDED, 1>;
+    case 12: return fa_fwd_kernel<12, BOUNDED, 1>;
+    default: return fa_fwd_kernel<8, BOUNDED, 1>;
   }
 }
 
-}  // namespace bya
-
-extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo,
-                                 int batch, int seq, int heads, float scale) {
-  using namespace bya;
+template <bool BOUNDED>
+static int fa_launch(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo, int batch,
+                     int seq, int heads, float scale) {
   if (!q || !k || !v || !out || batch <= 0 || seq <= 0 || heads <= 0) return BYA_ERR_SHAPE;
   if (ld % 8 || ldo % 8 || ld < heads * FA_D || ldo < heads * FA_D) return BYA_ERR_ALIGN;
   const uint64_t rows = uint64_t(batch) * seq;
@@ -489,7 +583,7 @@ extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, con
   static FaKernel kern = nullptr;
   static int threads = 0;
   if (!kern) {
-    FaKernel kk = fa_pick_kernel(&threads);
+    FaKernel kk = fa_pick_kernel<BOUNDED>(&threads);
     if (cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess)
       return BYA_ERR_CUDA;
     kern = kk;
@@ -501,7 +595,22 @@ extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, con
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.trace = nullptr;
+  if (const char* e = std::getenv("BYA_FA_TRACE")) a.trace = reinterpret_cast<long long*>(std::strtoull(e, nullptr, 0));
   dim3 grid((seq + 2 * FA_BM - 1) / (2 * FA_BM), heads, batch);
   kern<<<grid, threads, FA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
+}
+
+}  // namespace bya
+
+extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo,
+                                 int batch, int seq, int heads, float scale) {
+  return bya::fa_launch<false>(stream, q, k, v, ld, out, ldo, batch, seq, heads, scale);
+}
+
+extern "C" int bya_attention_d64_bounded(void* stream, const void* q, const void* k, const void* v, int ld, void* out,
+                                         int ldo, int batch, int seq, int heads, float score_bound_log2) {
+  if (!(score_bound_log2 > 0.f) || score_bound_log2 > 64.f) return BYA_ERR_SHAPE;   // also rejects NaN
+  return bya::fa_launch<true>(stream, q, k, v, ld, out, ldo, batch, seq, heads, 1.0f);
 }

@@ -217,6 +217,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 v[i + 3] = x3 * c4.w + x2 * s4.w;
               }
             }
+            if (!is_k && p.q_premul != 0.f) {   // softmax scale * log2(e) folded into q (bya_attention_d64_bounded)
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] *= p.q_premul;
+            }
           }
           if (row_ok) {
             uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldc + out_col(col));

@@ -172,9 +172,18 @@ class StepEngine:
         m, D = self.model, self.D
         self.layers = []
         ada_w, ada_b = [], []
+        # softmax scale * log2(e), folded into q by the QKV epilogue when the bounded attention kernel is used
+        hd = m.config.attention_head_dim
+        self.q_premul = hd ** -0.5 * math.log2(math.e)
         for blk in m.transformer_blocks:
             a = blk.attn1
+            # |q.k| bound from the per-head LayerNorm (|LN(x)|_2 <= sqrt(64); RoPE is a rotation): lets the joint
+            # self-attention run without a running max (bya_attention_d64_bounded); 2 % margin for bf16 rounding
+            qn = math.sqrt(hd) * float(a.norm_q.weight.float().abs().max()) + float(a.norm_q.bias.float().norm())
+            kn = math.sqrt(hd) * float(a.norm_k.weight.float().abs().max()) + float(a.norm_k.bias.float().norm())
+            bound = 1.02 * qn * kn * self.q_premul + 1e-3
             self.layers.append(dict(
+                score_bound=bound if (bound <= 64.0 and getattr(m, "bounded_attention", True)) else None,
                 w_qkv=_bf(torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight], 0)),
                 b_qkv=_bf(torch.cat([a.to_q.bias, a.to_k.bias, a.to_v.bias], 0)) if a.to_q.bias is not None else None,
                 nq=(_bf(a.norm_q.weight), _bf(a.norm_q.bias)), nk=(_bf(a.norm_k.weight), _bf(a.norm_k.bias)),
@@ -468,17 +477,21 @@ class StepEngine:
                 # ---- DiT block (transformer.py:223-262)
                 ops.layernorm_modulate(x, xn, eps=L["ln1"][2], gamma=L["ln1"][0], beta=L["ln1"][1], mod_a=(esc, esh),
                                        mod_b=(sc, sh), split_row=Tl)
+                sb = L["score_bound"]
+                qpm = self.q_premul if sb is not None else 0.0
                 if P == 1:
                     ops.gemm(xn, L["w_qkv"], qkv, bias=L["b_qkv"], mode=ops.EPI_QKV, split_row=Tl, ln_eps=L["qk_eps"],
-                             rope=(cos, sin), nq=L["nq"], nk=L["nk"])
-                    ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, 1, N, self.heads, tag="self_attention")
+                             rope=(cos, sin), nq=L["nq"], nk=L["nk"], q_premul=qpm)
+                    ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, 1, N, self.heads, tag="self_attention",
+                                      score_bound_log2=sb)
                     ops.gemm(att, L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g, split_row=Tl)
                 else:
                     ops.gemm(xn, L["w_qkv_sp"], qkv_send[0], bias=L["b_qkv_sp"], mode=ops.EPI_QKV, split_row=Tl,
                              ln_eps=L["qk_eps"], rope=(cos, sin), rope_row0=v0, nq=L["nq"], nk=L["nk"], qkv_block=3 * Dl,
-                             col_block=3 * Dl, col_block_stride=R * 3 * Dl)
+                             col_block=3 * Dl, col_block_stride=R * 3 * Dl, q_premul=qpm)
                     dist.all_to_all_single(qkv.view(P, R, 3 * Dl), qkv_send, group=self.sp_group)
-                    ops.attention_d64(qkv[:, :Dl], qkv[:, Dl:2 * Dl], qkv[:, 2 * Dl:], o_send, 1, N, Hl_, tag="self_attention")
+                    ops.attention_d64(qkv[:, :Dl], qkv[:, Dl:2 * Dl], qkv[:, 2 * Dl:], o_send, 1, N, Hl_, tag="self_attention",
+                                      score_bound_log2=sb)
                     dist.all_to_all_single(o_recv, o_send.view(P, R, Dl), group=self.sp_group)
                     ops.gemm(o_recv[0], L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g,
                              split_row=Tl, a_kblock=Dl, a_kblock_stride=R * Dl)

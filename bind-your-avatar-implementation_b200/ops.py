@@ -45,7 +45,7 @@ def _bf16_2d(t: torch.Tensor, name: str):
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=ACT_NONE, mode=EPI_STORE,
          resid=None, gate_a=None, gate_b=None, split_row=0, alpha=1.0, row_bias_scale=None,
          qkv_block=0, ln_eps=1e-6, rope=None, rope_row0=0, nq=None, nk=None, group_m=0, col_block=0,
-         col_block_stride=0, a_kblock=0, a_kblock_stride=0) -> torch.Tensor:
+         col_block_stride=0, a_kblock=0, a_kblock_stride=0, q_premul=0.0) -> torch.Tensor:
     """out = epilogue(a @ w.T); a [M,K], w [N,K], out [M,N] (row strides may exceed the width).
     With a_kblock: `a` is the first [M, a_kblock] block of K/a_kblock blocks a_kblock_stride elements apart.
     With col_block: `out` is the first [M, col_block] block of N/col_block blocks col_block_stride elements apart."""
@@ -76,6 +76,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
         args.nq_w, args.nq_b, args.nk_w, args.nk_b = _ptr(nq[0]), _ptr(nq[1]), _ptr(nk[0]), _ptr(nk[1])
     args.col_block, args.col_block_stride = col_block, col_block_stride
     args.a_kblock, args.a_kblock_stride = a_kblock, a_kblock_stride
+    args.q_premul = q_premul
     rc = lib().bya_gemm_bf16(_stream(), _ptr(a), a.stride(0), _ptr(w), w.stride(0), ctypes.byref(args))
     check(rc, "gemm")
     LAUNCHES += 1
@@ -83,8 +84,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
 
 
 def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, batch: int, seq: int,
-                  heads: int, scale: float = 0.125, tag=None) -> torch.Tensor:
-    """q/k/v/out: [batch*seq, heads*64] column-slice views (shared row stride for q,k,v) of bf16 matrices."""
+                  heads: int, scale: float = 0.125, tag=None, score_bound_log2: Optional[float] = None) -> torch.Tensor:
+    """q/k/v/out: [batch*seq, heads*64] column-slice views (shared row stride for q,k,v) of bf16 matrices.
+    With `score_bound_log2` (<= 64): q is pre-scaled so that q.k is in log2 units and |q.k| <= the bound
+    (`bya_attention_d64_bounded`); `scale` is then ignored."""
     global LAUNCHES
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _bf16_2d(t, n)
@@ -93,8 +96,12 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.
     if not (q.stride(0) == k.stride(0) == v.stride(0)):
         raise RuntimeError("bya_b200.attention_d64: q, k, v must share a row stride")
     ev = _prof(tag)
-    rc = lib().bya_attention_d64(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
-                                 batch, seq, heads, ctypes.c_float(scale))
+    if score_bound_log2 is not None:
+        rc = lib().bya_attention_d64_bounded(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
+                                             batch, seq, heads, ctypes.c_float(score_bound_log2))
+    else:
+        rc = lib().bya_attention_d64(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
+                                     batch, seq, heads, ctypes.c_float(scale))
     if ev is not None:
         ev.record()
     check(rc, "attention_d64")

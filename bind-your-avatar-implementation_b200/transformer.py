@@ -130,6 +130,7 @@ class BindyouravatarTransformer3DModel(nn.Module):
         self._engine_sig = None
         self._processors: Dict[str, Any] = {}
         self.cache_prologue = True
+        self.bounded_attention = True  # joint self-attention without a running max when the qk-LayerNorm bounds |q.k|
         self.use_cuda_graph = False  # replay the step as one CUDA graph per input geometry (engine.step_graphed)
         self._sp_group = None  # set by bya_b200.sp.enable(): Ulysses sequence parallelism over this process group
 

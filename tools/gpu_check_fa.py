@@ -9,26 +9,40 @@ from bya_b200 import ops
 torch.manual_seed(0)
 dev = "cuda"
 
+BOUNDED = os.environ.get("BOUNDED", "0") == "1"
+
+def attn(q, k, v, out, batch, seq, heads):
+    if BOUNDED:   # q pre-scaled to log2 units, |q.k| <= 64 by construction below
+        ops.attention_d64(q, k, v, out, batch, seq, heads, score_bound_log2=64.0)
+    else:
+        ops.attention_d64(q, k, v, out, batch, seq, heads)
+
 def run(batch, seq, heads, qscale=1.0, check=True, iters=0):
     D = heads * 64
     qkv = (torch.randn(batch * seq, 3 * D, device=dev) * qscale).bfloat16()
+    if BOUNDED:   # unit-norm-ish q/k heads like the qk-LayerNorm output (|q| = |k| = 8), q times scale*log2(e)
+        x = qkv.float().reshape(batch * seq, 3 * heads, 64)
+        x[:, :2 * heads] = torch.nn.functional.layer_norm(x[:, :2 * heads], (64,)) * min(qscale, 1.5)
+        x[:, :heads] *= 0.125 * 1.4426950408889634
+        qkv = x.reshape(batch * seq, 3 * D).bfloat16()
     q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
     out = torch.zeros(batch * seq, D, device=dev, dtype=torch.bfloat16)
-    ops.attention_d64(q, k, v, out, batch, seq, heads)
+    attn(q, k, v, out, batch, seq, heads)
     torch.cuda.synchronize()
     ok = True
     if check:
         def hv(x): return x.reshape(batch, seq, heads, 64).transpose(1, 2).float()
-        ref = F.scaled_dot_product_attention(hv(q), hv(k), hv(v)).transpose(1, 2).reshape(batch * seq, D)
+        sc = 0.6931471805599453 if BOUNDED else None   # softmax_2(s) = softmax(s ln 2)
+        ref = F.scaled_dot_product_attention(hv(q), hv(k), hv(v), scale=sc).transpose(1, 2).reshape(batch * seq, D)
         err = (out.float() - ref).abs().max().item()
         rel = err / ref.abs().max().item()
         ok = rel < 2e-2 and bool(torch.isfinite(out.float()).all())
         print(f"fa batch={batch} seq={seq} heads={heads} qscale={qscale}: max_abs={err:.3e} rel={rel:.3e}", "OK" if ok else "FAIL", flush=True)
     if iters:
-        for _ in range(2): ops.attention_d64(q, k, v, out, batch, seq, heads)
+        for _ in range(2): attn(q, k, v, out, batch, seq, heads)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); s.record()
-        for _ in range(iters): ops.attention_d64(q, k, v, out, batch, seq, heads)
+        for _ in range(iters): attn(q, k, v, out, batch, seq, heads)
         e.record(); torch.cuda.synchronize()
         ms = s.elapsed_time(e) / iters
         fl = 4.0 * batch * heads * seq * seq * 64 / 1e9
