@@ -23,15 +23,18 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
                      uint32_t box_inner, uint32_t box_rows, uint64_t batch, uint64_t batch_stride_bytes) {
   auto enc = get_encode();
   if (!enc) return BYA_ERR_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_bytes & 15) || box_inner * 2 != 128 || box_rows > 256)
+  // inner box of 128 B -> 128B swizzle (operand tiles), 64 B -> 64B swizzle (epilogue staging tiles)
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_bytes & 15) || (batch_stride_bytes & 15) ||
+      (box_inner * 2 != 128 && box_inner * 2 != 64) || box_rows > 256)
     return BYA_ERR_ALIGN;
+  const CUtensorMapSwizzle swz = box_inner * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const bool three_d = batch > 1;
   cuuint64_t dims[3] = {inner, rows, batch};
   cuuint64_t strides[2] = {row_stride_bytes, batch_stride_bytes};
   cuuint32_t box[3] = {box_inner, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, three_d ? 3 : 2, const_cast<void*>(base), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? BYA_OK : BYA_ERR_DRIVER;
 }

@@ -4,8 +4,12 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled tiles, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       (tcgen05.ld -> registers -> fused epilogue -> global), double-buffered against the
-//                              next tile's main loop through two TMEM accumulator stages
+//   warps 4..11 epilogue       (tcgen05.ld -> registers -> fused epilogue -> global), double-buffered against the
+//                              next tile's main loop through two TMEM accumulator stages.  Two warps per TMEM lane
+//                              quarter (each takes half of the tile's columns); the tile's bias and gate vectors are
+//                              staged in shared memory BEFORE the accumulator is awaited and the residual is
+//                              prefetched one chunk ahead: the K=512 router GEMMs were bound by exactly these
+//                              global-load latencies (ncu: epilogue warps in long_sb on the bias loads)
 // Replaces, on the hot path, every nn.Linear of the reference's denoising step:
 // models/transformer.py:200-221 (attn1.to_q/k/v/to_out, ff), models/router.py:226-228,301-302,430-466,
 // models/audio_model.py:179-185.  The fused epilogues replace the elementwise ops the reference runs after them:
@@ -14,26 +18,40 @@
 #include "common.cuh"
 #include "gemm.h"
 
+#include <cstdlib>
+
 namespace bya {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kStages = 4;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
 
 template <int BN>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kEpiOffset = kStages * kStageBytes;          // [2 stages][bias | gate_a | gate_b][BN] fp32
+  static constexpr int kEpiBytes = 2 * 3 * BN * 4;
+  static constexpr int kStgOffset = kEpiOffset + ((kEpiBytes + 1023) / 1024) * 1024;   // [8 warps][32 rows x 64 B], 64B-swizzled
+  static constexpr int kStgBytes = 8 * 2048;
+  static constexpr int kBarOffset = kStgOffset + kStgBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + slack for 1024 B alignment
 };
+
+// debug timeline (BYA_GEMM_TRACE=<device pointer>): clock64 stamps of CTA 0, event e of its i-th tile (i < 16)
+__device__ long long* g_gemm_trace = nullptr;
+#define GEMM_TRACE(e, i)                                                                  \
+  do {                                                                                    \
+    if (g_gemm_trace && blockIdx.x == 0 && (i) < 16 && lane == 0) g_gemm_trace[(i) * 8 + (e)] = clock64(); \
+  } while (0)
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmArgs p) {
+                 const __grid_constant__ CUtensorMap tmap_c, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = GemmSmem<BN>;
@@ -54,6 +72,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -62,7 +81,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -90,11 +109,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int ti = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
         int mb, nb;
         tile_coord(t, mb, nb);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (kb == 0) GEMM_TRACE(0, ti);
+          if (kb == num_kb - 1) GEMM_TRACE(1, ti);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
@@ -116,12 +138,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    int ti = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
       mbar_wait(&tempty_bar[as], aphase ^ 1);
+      GEMM_TRACE(2, ti);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
+        if (kb == 0) GEMM_TRACE(3, ti);
+        if (kb == num_kb - 1) GEMM_TRACE(4, ti);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
@@ -142,22 +168,59 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;    // which half of the tile's columns
+    const int et = threadIdx.x - 128;    // 0..255
+    float* epi = reinterpret_cast<float*>(smem + L::kEpiOffset);
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    int ti = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
       int mb, nb;
       tile_coord(t, mb, nb);
+      const int col0 = nb * BN;
+      if (warp == 4) GEMM_TRACE(5, ti);
+      // stage this tile's column vectors while the main loop is still running
+      float* sbias = epi + as * 3 * BN;
+      float* sga = sbias + BN;
+      float* sgb = sga + BN;
+      for (int i = et; i < BN; i += kEpiThreads) {
+        sbias[i] = p.bias ? __bfloat162float(p.bias[col0 + i]) : 0.f;
+        if (p.mode == GEMM_EPI_RESIDUAL) {
+          sga[i] = p.gate_a ? p.gate_a[col0 + i] : 1.f;
+          sgb[i] = p.gate_b ? p.gate_b[col0 + i] : 1.f;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tfull_bar[as], aphase);
+      if (warp == 4) GEMM_TRACE(6, ti);
       tc_fence_after();
       const int row = mb * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + as * BN + (uint32_t(q * 32) << 16);
-      const int col0 = nb * BN;
-      // output column -> element offset within a row (column-block scatter for the sequence-parallel send buffer)
-      auto out_col = [&](int col) -> size_t {
-        return p.col_block ? size_t(col / p.col_block) * size_t(p.col_block_stride) + size_t(col % p.col_block)
-                           : size_t(col);
+      // Output: 32 rows x 32 columns per warp and chunk -> shared memory (64B-swizzled, conflict-free 16 B stores)
+      // -> ONE TMA store.  A thread owns an accumulator ROW, so direct global stores put 32 different rows (32
+      // half-written sectors) into every store instruction: the clock64 timeline showed 10.8k cycles of epilogue
+      // per 128x256 tile, 2.6x the K=512 main loop.  TMA clips rows >= M; with col_block (sequence-parallel send
+      // buffer) the map is 3-D [dest][row][col].
+      uint8_t* stg = smem + L::kStgOffset + (warp - 4) * 2048;
+      const uint32_t stg_row = smem_u32(stg) + lane * 64;
+      const int row0 = mb * BM + q * 32;
+      auto store32 = [&](const float* v, int col) {
+        if (lane == 0) tma_store_wait_read<0>();   // the previous chunk's store has finished reading the buffer
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(stg_row + (((j ^ (lane >> 1)) & 3) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]),
+                       pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                       pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.col_block) tma_store_3d(&tmap_c, stg, col % p.col_block, row0, col / p.col_block);
+          else tma_store_2d(&tmap_c, stg, col, row0);
+          tma_store_commit();
+        }
       };
 
       if (p.mode == GEMM_EPI_QKV) {
@@ -166,8 +229,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const float* cs = p.rope_cos + size_t(max(row - p.split_row, 0) + p.rope_row0) * 64;
         const float* sn = p.rope_sin + size_t(max(row - p.split_row, 0) + p.rope_row0) * 64;
         const int blk = p.qkv_block ? p.qkv_block : p.N;
+        constexpr int HC = (BN / 2 >= 64) ? BN / 2 : 64;   // columns per warp (whole heads)
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
+        for (int c = half * HC; c < (half + 1) * HC && c < BN; c += 64) {
           uint32_t r[64];
           tmem_ld_x32(taddr + c, r);
           tmem_ld_x32(taddr + c + 32, r + 32);
@@ -175,16 +239,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int col = col0 + c;
           float v[64];
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
-            float b0 = 0.f, b1 = 0.f;
-            if (p.bias) {
-              uint32_t bb = *reinterpret_cast<const uint32_t*>(p.bias + col + i);
-              b0 = bf16_lo(bb);
-              b1 = bf16_hi(bb);
-            }
-            v[i] = __uint_as_float(r[i]) + b0;
-            v[i + 1] = __uint_as_float(r[i + 1]) + b1;
-          }
+          for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]) + sbias[c + i];
           const int cin = col % blk;  // position inside the [q|k|v] group
           if (3 * cin < 2 * blk) {
             const bool is_k = 3 * cin >= blk;
@@ -222,90 +277,75 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int i = 0; i < 64; ++i) v[i] *= p.q_premul;
             }
           }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldc + out_col(col));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
-              o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-              o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-              o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-              dst[i] = o;
-            }
-          }
+          store32(v, col);
+          store32(v + 32, col + 32);
         }
       } else {
         const float* gate = nullptr;
         float rscale = p.alpha;
         float bscale = 1.f;
-        if (p.mode == GEMM_EPI_RESIDUAL) {
-          gate = (row < p.split_row) ? p.gate_a : p.gate_b;
+        const bool resid_mode = p.mode == GEMM_EPI_RESIDUAL;
+        if (resid_mode) {
+          gate = (row < p.split_row) ? sga : sgb;
           if (p.row_bias_scale && row_ok) bscale = p.row_bias_scale[row];
         }
-        constexpr int CH = (BN >= 32) ? 32 : BN;
+        constexpr int CH = (BN >= 64) ? 32 : BN / 2;   // columns per chunk; each warp owns BN/2 columns
+        constexpr int NCH = (BN / 2) / CH;
+        const int cbeg = half * (BN / 2);
+        const __nv_bfloat16* rrow = resid_mode ? p.resid + size_t(row_ok ? row : 0) * p.ldr + col0 + cbeg : nullptr;
+        uint4 rnext[CH / 8];
+        if (resid_mode) {
+#pragma unroll
+          for (int i = 0; i < CH / 8; ++i) rnext[i] = reinterpret_cast<const uint4*>(rrow)[i];
+        }
 #pragma unroll 1
-        for (int c = 0; c < BN; c += CH) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c, r);
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = cbeg + ci * CH;
+          uint32_t r[CH];
+          if (CH == 32) tmem_ld_x32(taddr + c, r);
+          else tmem_ld_x16(taddr + c, r);
+          uint4 rcur[CH / 8];
+          if (resid_mode) {
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) rcur[i] = rnext[i];
+            if (ci + 1 < NCH) {   // prefetch the next chunk's residual under this chunk's math
+#pragma unroll
+              for (int i = 0; i < CH / 8; ++i) rnext[i] = reinterpret_cast<const uint4*>(rrow + (ci + 1) * CH)[i];
+            }
+          }
           tmem_ld_wait();
           const int col = col0 + c;
-          float v[32];
+          float v[CH];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float b0 = 0.f, b1 = 0.f;
-            if (p.bias) {
-              uint32_t bb = *reinterpret_cast<const uint32_t*>(p.bias + col + i);
-              b0 = bf16_lo(bb) * bscale;
-              b1 = bf16_hi(bb) * bscale;
-            }
-            v[i] = __uint_as_float(r[i]) + b0;
-            v[i + 1] = __uint_as_float(r[i + 1]) + b1;
-          }
+          for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]) + sbias[c + i] * bscale;
           if (p.act == GEMM_ACT_GELU_TANH) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+            for (int i = 0; i < CH; ++i) v[i] = gelu_tanh(v[i]);
           } else if (p.act == GEMM_ACT_GELU_ERF) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
           }
-          if (!row_ok) continue;
-          if (p.mode == GEMM_EPI_RESIDUAL) {
-            const uint4* rs = reinterpret_cast<const uint4*>(p.resid + size_t(row) * p.ldr + col);
+          if (resid_mode) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 x = rs[i];
-              const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+            for (int i = 0; i < CH / 8; ++i) {
+              const uint32_t xs[4] = {rcur[i].x, rcur[i].y, rcur[i].z, rcur[i].w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int e = 8 * i + 2 * j;
-                float g0 = rscale, g1 = rscale;
-                if (gate) {
-                  const float2 gg = *reinterpret_cast<const float2*>(gate + col + e);
-                  g0 *= gg.x;
-                  g1 *= gg.y;
-                }
-                v[e] = bf16_lo(xs[j]) + g0 * v[e];
-                v[e + 1] = bf16_hi(xs[j]) + g1 * v[e + 1];
+                v[e] = bf16_lo(xs[j]) + rscale * gate[c + e] * v[e];
+                v[e + 1] = bf16_hi(xs[j]) + rscale * gate[c + e + 1] * v[e + 1];
               }
             }
           }
-          uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldc + out_col(col));
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]);
-            o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-            o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-            o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-            dst[i] = o;
-          }
+          store32(v, col);
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
+      if (warp == 4) GEMM_TRACE(7, ti);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) tma_store_wait<0>();   // every output tile has landed before the CTA retires
   }
 
   tc_fence_before();
@@ -325,6 +365,11 @@ static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W,
   if (rc) return rc;
   rc = bya_host::encode_tmap_bf16(&tb, W, a.K, a.N, uint64_t(ldw) * 2, BK, BN);
   if (rc) return rc;
+  CUtensorMap tc;   // output: 32 x 32 boxes; with col_block a 3-D [dest][row][col] view of the send buffer
+  rc = a.col_block ? bya_host::encode_tmap_bf16(&tc, a.out, a.col_block, a.M, uint64_t(a.ldc) * 2, 32, 32, a.N / a.col_block,
+                                                uint64_t(a.col_block_stride) * 2)
+                   : bya_host::encode_tmap_bf16(&tc, a.out, a.N, a.M, uint64_t(a.ldc) * 2, 32, 32);
+  if (rc) return rc;
   auto kern = gemm_bf16_kernel<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -332,9 +377,17 @@ static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W,
       return BYA_ERR_CUDA;
     attr_set = true;
   }
+  static bool trace_set = false;
+  if (!trace_set) {
+    trace_set = true;
+    if (const char* e = std::getenv("BYA_GEMM_TRACE")) {
+      long long* ptr = reinterpret_cast<long long*>(std::strtoull(e, nullptr, 0));
+      cudaMemcpyToSymbol(g_gemm_trace, &ptr, sizeof(ptr));
+    }
+  }
   const int num_tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
   const int grid = num_tiles < bya_host::num_sms() ? num_tiles : bya_host::num_sms();
-  kern<<<grid, kThreads, GemmSmem<BN>::kTotal, stream>>>(ta, tb, a);
+  kern<<<grid, kThreads, GemmSmem<BN>::kTotal, stream>>>(ta, tb, tc, a);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }
 
@@ -357,6 +410,7 @@ extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W
   if (a.col_block && (a.col_block % 64 || a.N % a.col_block || a.col_block_stride % 8 || a.mode == GEMM_EPI_RESIDUAL))
     return BYA_ERR_SHAPE;
   if (a.a_kblock == a.K) a.a_kblock = 0;
+  if (a.col_block == a.N) a.col_block = 0;   // a single column block is the plain layout
   if (a.a_kblock && (a.a_kblock % BK || a.K % a.a_kblock || a.a_kblock_stride % 8)) return BYA_ERR_SHAPE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a.N % 256 == 0) return launch_gemm<256>(a, A, lda, W, ldw, s);
