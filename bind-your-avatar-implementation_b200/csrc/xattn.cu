@@ -163,79 +163,160 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Router temporal (L = frames) and multi-ID (L = characters) self-attention, 8 heads x 64 (router.py:478-488).
-// A "sequence" is L rows of the [rows, 3*HD] qkv matrix spaced `tok_stride` rows apart, starting at
-//   base(s) = (s / inner) * outer_stride + (s % inner).
-// One THREAD per (query row, head): the 64-wide q, the running output and the online-softmax state live in
-// registers; K/V rows are streamed with 16-byte loads (the L rows of a sequence are shared by its L query threads
-// through L1).  Adjacent threads are adjacent heads of the same row, so every warp load is 4 rows x 1 KB contiguous.
-__global__ void __launch_bounds__(128)
+// Router temporal / multi-ID self-attention (models/router.py:478-488): many independent tiny sequences (L = 13
+// frames, or L = C characters) of rows of the [rows, 3*heads*64] qkv matrix; rows of sequence s are tok_stride apart,
+// its first row is  base(s) = (s / inner) * outer_stride + (s % inner).
+// One WARP per (group of 16/L consecutive sequences, head): their <= 16 q, k and v rows (128 B each) are read ONCE
+// with 16-byte coalesced loads into a padded shared tile (short sequences share a tile and are kept apart by a
+// block-diagonal mask), S = Q K^T and O = P V run as m16n8k16 mma.sync tiles fed by ldmatrix, the softmax stays
+// in the accumulator registers, and the L output rows leave through the same tile with 16-byte stores.
+// HBM-bound: qkv is read once (108 MB per call at the c2 size) and out written once (36 MB).  The first version
+// (one thread per query row) re-read every K/V row L times from L2 and took 143-180 us per call; the roofline of
+// the call is 22 us.
+constexpr int SA_WARPS = 4;
+constexpr int SA_PITCH = 72;   // bf16 elements per shared row: 144 B keeps ldmatrix and 16 B accesses conflict-free
+
+BYA_DEVICE void ldmatrix_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+BYA_DEVICE void ldmatrix_x4_trans(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(SA_WARPS * 32)
 small_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, __nv_bfloat16* __restrict__ out, int ldo,
                        int n_seq, int L, int heads, int inner, long long outer_stride, long long tok_stride,
                        float scale_log2) {
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n_seq * L * heads;
-  if (tid >= total) return;
-  const int h = int(tid % heads);
-  const long long si = tid / heads;
-  const int s = int(si % n_seq), i = int(si / n_seq);
-  const long long base = (long long)(s / inner) * outer_stride + (s % inner);
+  __shared__ __align__(16) __nv_bfloat16 tile[SA_WARPS][3][16][SA_PITCH];   // q | k | v, rows >= L zero
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int spw = 16 / L;                                                    // sequences per warp tile
+  const int rows = spw * L;
+  const long long unit = (long long)blockIdx.x * SA_WARPS + warp;            // (sequence group, head), heads fastest
+  if (unit >= (long long)((n_seq + spw - 1) / spw) * heads) return;
+  const int h = int(unit % heads);
+  const int s0 = int(unit / heads) * spw;
   const int HD = heads * 64;
-  float q[64], acc[64];
+  // tile row r = (sequence s0 + r / L, position r % L) -> row of qkv / out (-1: padding)
+  auto grow = [&](int r) -> long long {
+    const int si = r / L, s = s0 + si;
+    if (r >= rows || s >= n_seq) return -1;
+    return (long long)(s / inner) * outer_stride + (s % inner) + (long long)(r - si * L) * tok_stride;
+  };
+  __nv_bfloat16 (*T)[16][SA_PITCH] = tile[warp];
+
+  // ---- load: lane -> (row = lane / 8 + 4 i, 16-byte chunk = lane % 8): 4 rows x 128 B per instruction
+  long long gr[4];
   {
-    const uint4* qp = reinterpret_cast<const uint4*>(qkv + size_t(base + i * tok_stride) * ld + h * 64);
+    const int ch = lane & 7;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = qp[c];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int i = 0; i < 4; ++i) gr[i] = grow((lane >> 3) + 4 * i);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        q[c * 8 + 2 * e] = bf16_lo(w[e]) * scale_log2;
-        q[c * 8 + 2 * e + 1] = bf16_hi(w[e]) * scale_log2;
+    for (int m = 0; m < 3; ++m) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (lane >> 3) + 4 * i;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (gr[i] >= 0) v = *reinterpret_cast<const uint4*>(qkv + size_t(gr[i]) * ld + m * HD + h * 64 + ch * 8);
+        *reinterpret_cast<uint4*>(&T[m][r][ch * 8]) = v;
       }
     }
   }
+  __syncwarp();
+
+  const int g = lane >> 2, t = lane & 3;
+  // ---- S = Q K^T  (16 x 16, two n-tiles of 8 keys), k-dim = 64 in 4 steps
+  float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  {
+    // ldmatrix.x4 address pattern: lanes 0-15 -> rows 0-15 of the left 8 columns, lanes 16-31 -> the right 8 columns
+    const uint32_t qa = smem_u32(&T[0][lane & 15][(lane >> 4) * 8]);
+    // K as the col-major B operand: matrices (keys 0-7, d 0-7), (keys 0-7, d 8-15), (keys 8-15, d 0-7), (keys 8-15, d 8-15)
+    const uint32_t ka = smem_u32(&T[1][(lane & 7) + ((lane >> 4) << 3)][((lane >> 3) & 1) * 8]);
 #pragma unroll
-  for (int d = 0; d < 64; ++d) acc[d] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  for (int j = 0; j < L; ++j) {
-    const __nv_bfloat16* row = qkv + size_t(base + j * tok_stride) * ld + h * 64;
-    const uint4* kp = reinterpret_cast<const uint4*>(row + HD);
-    float sc = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = kp[c];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) sc += q[c * 8 + 2 * e] * bf16_lo(w[e]) + q[c * 8 + 2 * e + 1] * bf16_hi(w[e]);
-    }
-    const float mn = fmaxf(m, sc);
-    const float a = exp2f(m - mn), pj = exp2f(sc - mn);
-    m = mn;
-    l = l * a + pj;
-    const uint4* vp = reinterpret_cast<const uint4*>(row + 2 * HD);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = vp[c];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        acc[c * 8 + 2 * e] = acc[c * 8 + 2 * e] * a + pj * bf16_lo(w[e]);
-        acc[c * 8 + 2 * e + 1] = acc[c * 8 + 2 * e + 1] * a + pj * bf16_hi(w[e]);
-      }
+    for (int k = 0; k < 4; ++k) {
+      uint32_t a[4], b[4];
+      ldmatrix_x4(a, qa + k * 32);
+      ldmatrix_x4(b, ka + k * 32);
+      mma_bf16_16816(sc[0], a, b[0], b[1]);
+      mma_bf16_16816(sc[1], a, b[2], b[3]);
     }
   }
-  const float inv = 1.f / l;
-  uint4* op = reinterpret_cast<uint4*>(out + size_t(base + i * tok_stride) * ldo + h * 64);
+  // ---- softmax over the L valid keys (rows g and g + 8 of the accumulator; a row lives in one quad)
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  const int rs0 = g / L, rs1 = (g + 8) / L;   // which sequence of the tile rows g and g + 8 belong to
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint4 o;
-    o.x = pack_bf16x2(acc[c * 8] * inv, acc[c * 8 + 1] * inv);
-    o.y = pack_bf16x2(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
-    o.z = pack_bf16x2(acc[c * 8 + 4] * inv, acc[c * 8 + 5] * inv);
-    o.w = pack_bf16x2(acc[c * 8 + 6] * inv, acc[c * 8 + 7] * inv);
-    op[c] = o;
+  for (int n = 0; n < 2; ++n) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = n * 8 + 2 * t + e;         // key column: only keys of the query's own sequence count
+      const int cs = c / L;
+      sc[n][e] = (c < rows && cs == rs0) ? sc[n][e] * scale_log2 : -INFINITY;
+      sc[n][2 + e] = (c < rows && cs == rs1) ? sc[n][2 + e] * scale_log2 : -INFINITY;
+      mx0 = fmaxf(mx0, sc[n][e]);
+      mx1 = fmaxf(mx1, sc[n][2 + e]);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  mx0 = (mx0 == -INFINITY) ? 0.f : mx0;       // padding rows: no valid key
+  mx1 = (mx1 == -INFINITY) ? 0.f : mx1;
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      sc[n][e] = exp2f(sc[n][e] - mx0);
+      sc[n][2 + e] = exp2f(sc[n][2 + e] - mx1);
+      l0 += sc[n][e];
+      l1 += sc[n][2 + e];
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // P as the A operand of O = P V (k = 16 keys): accumulator layout == A-fragment layout
+  uint32_t pa[4];
+  pa[0] = pack_bf16x2(sc[0][0], sc[0][1]);
+  pa[1] = pack_bf16x2(sc[0][2], sc[0][3]);
+  pa[2] = pack_bf16x2(sc[1][0], sc[1][1]);
+  pa[3] = pack_bf16x2(sc[1][2], sc[1][3]);
+  // ---- O = P V : 8 n-tiles of 8 head-dims; V[key][d] is the row-major [k][n] operand -> ldmatrix.trans
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  {
+    // matrices: (keys 0-7, d 0-7), (keys 8-15, d 0-7), (keys 0-7, d 8-15), (keys 8-15, d 8-15)
+    const uint32_t va = smem_u32(&T[2][(lane & 7) + (((lane >> 3) & 1) << 3)][(lane >> 4) * 8]);
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, va + n2 * 32);
+      mma_bf16_16816(o[2 * n2], pa, b[0], b[1]);
+      mma_bf16_16816(o[2 * n2 + 1], pa, b[2], b[3]);
+    }
+  }
+  // ---- normalise, stage through the (now dead) q tile, store L rows with 16-byte accesses
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    *reinterpret_cast<uint32_t*>(&T[0][g][n * 8 + 2 * t]) = pack_bf16x2(o[n][0] * i0, o[n][1] * i0);
+    *reinterpret_cast<uint32_t*>(&T[0][g + 8][n * 8 + 2 * t]) = pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
+  }
+  __syncwarp();
+  {
+    const int ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (lane >> 3) + 4 * i;
+      if (gr[i] >= 0)
+        *reinterpret_cast<uint4*>(out + size_t(gr[i]) * ldo + h * 64 + ch * 8) =
+            *reinterpret_cast<const uint4*>(&T[0][r][ch * 8]);
+    }
   }
 }
 
@@ -282,11 +363,12 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
 
 extern "C" int bya_small_attention(void* stream, const void* qkv, int ld, void* out, int ldo, int n_seq, int seq_len,
                                    int heads, int inner, long long outer_stride, long long tok_stride, float scale) {
-  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0 || inner <= 0) return BYA_ERR_SHAPE;
+  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || seq_len > 16 || heads <= 0 || inner <= 0) return BYA_ERR_SHAPE;
   if (ld % 8 || ldo % 8) return BYA_ERR_ALIGN;
-  const long long threads = (long long)n_seq * seq_len * heads;
-  const int blocks = int((threads + 127) / 128);
-  small_attention_kernel<<<blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  const int spw = 16 / seq_len;
+  const long long units = (long long)((n_seq + spw - 1) / spw) * heads;
+  const int blocks = int((units + SA_WARPS - 1) / SA_WARPS);
+  small_attention_kernel<<<blocks, SA_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq, seq_len, heads, inner, outer_stride, tok_stride,
       scale * 1.4426950408889634f);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
