@@ -368,7 +368,12 @@ def main():
             "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": nbytes(out_host)},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "fa_fwd_kernel (joint self-attention)", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the ncu --set full
+                         # capture summarised in profiles/r1_summary.md (algorithmic: 436.8 MB = qkv read + O write)
+                         "traffic": 447.8e6 if (world == 1 and args.config == "c2") else None, "traffic_unit": "bytes/launch",
+                         "how": "CUDA-event pairs around every self-attention launch on the launching stream, over 2 further "
+                                "eager steps of the same workload (events cannot bracket kernels inside a graph replay)",
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "launch_ms": fa_ms,
                          "step_tflops": _step_tflops(cfg) / (ms * 1e-3) / world, "step_frac_of_peak": _step_tflops(cfg) / (ms * 1e-3) / world / peak},
             "cpu_baseline": cpu_base,
