@@ -287,6 +287,7 @@ class BindyouravatarTransformer3DModel(nn.Module):
         eng = self.engine()
         if denoise_step == 0:
             eng._prologue_key = None  # a new generation: recompute the timestep-invariant prologue
+        # (sequence parallel stays eager: capturing the NCCL all-to-alls hung on the 2-GPU box in round 1)
         if self.use_cuda_graph and taps is None and self._sp_group is None:
             out = eng.step_graphed(hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,
                                    audio_embeds if self.is_train_audio else None, af_matrix,
