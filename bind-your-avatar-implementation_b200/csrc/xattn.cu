@@ -166,7 +166,7 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
 // Router temporal / multi-ID self-attention (models/router.py:478-488): many independent tiny sequences (L = 13
 // frames, or L = C characters) of rows of the [rows, 3*heads*64] qkv matrix; rows of sequence s are tok_stride apart,
 // its first row is  base(s) = (s / inner) * outer_stride + (s % inner).
-// One WARP per (group of 16/L consecutive sequences, head): their <= 16 q, k and v rows (128 B each) are read ONCE
+// One WARP per (group of consecutive sequences filling a 16- or 32-row tile, head): their q, k and v rows (128 B each) are read ONCE
 // with 16-byte coalesced loads into a padded shared tile (short sequences share a tile and are kept apart by a
 // block-diagonal mask), S = Q K^T and O = P V run as m16n8k16 mma.sync tiles fed by ldmatrix, the softmax stays
 // in the accumulator registers, and the L output rows leave through the same tile with 16-byte stores.
@@ -185,15 +185,18 @@ BYA_DEVICE void ldmatrix_x4_trans(uint32_t* r, uint32_t addr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-__global__ void __launch_bounds__(SA_WARPS * 32)
+template <int MT>   // MT 16-row tiles per warp: sequences of up to 16 * MT rows
+__global__ void __launch_bounds__(SA_WARPS * 32 / MT)
 small_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, __nv_bfloat16* __restrict__ out, int ldo,
                        int n_seq, int L, int heads, int inner, long long outer_stride, long long tok_stride,
                        float scale_log2) {
-  __shared__ __align__(16) __nv_bfloat16 tile[SA_WARPS][3][16][SA_PITCH];   // q | k | v, rows >= L zero
+  constexpr int R = 16 * MT;        // tile rows
+  constexpr int NW = SA_WARPS / MT; // warps per block (static shared memory stays under 48 KB)
+  __shared__ __align__(16) __nv_bfloat16 tile[NW][3][R][SA_PITCH];   // q | k | v, padding rows zero
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int spw = 16 / L;                                                    // sequences per warp tile
+  const int spw = R / L;                                                     // sequences per warp tile
   const int rows = spw * L;
-  const long long unit = (long long)blockIdx.x * SA_WARPS + warp;            // (sequence group, head), heads fastest
+  const long long unit = (long long)blockIdx.x * NW + warp;                  // (sequence group, head), heads fastest
   if (unit >= (long long)((n_seq + spw - 1) / spw) * heads) return;
   const int h = int(unit % heads);
   const int s0 = int(unit / heads) * spw;
@@ -204,18 +207,18 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, __nv_bfloa
     if (r >= rows || s >= n_seq) return -1;
     return (long long)(s / inner) * outer_stride + (s % inner) + (long long)(r - si * L) * tok_stride;
   };
-  __nv_bfloat16 (*T)[16][SA_PITCH] = tile[warp];
+  __nv_bfloat16 (*T)[R][SA_PITCH] = tile[warp];
 
   // ---- load: lane -> (row = lane / 8 + 4 i, 16-byte chunk = lane % 8): 4 rows x 128 B per instruction
-  long long gr[4];
+  long long gr[4 * MT];
   {
     const int ch = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) gr[i] = grow((lane >> 3) + 4 * i);
+    for (int i = 0; i < 4 * MT; ++i) gr[i] = grow((lane >> 3) + 4 * i);
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 4 * MT; ++i) {
         const int r = (lane >> 3) + 4 * i;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (gr[i] >= 0) v = *reinterpret_cast<const uint4*>(qkv + size_t(gr[i]) * ld + m * HD + h * 64 + ch * 8);
@@ -226,8 +229,12 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, __nv_bfloa
   __syncwarp();
 
   const int g = lane >> 2, t = lane & 3;
-  // ---- S = Q K^T  (16 x 16, two n-tiles of 8 keys), k-dim = 64 in 4 steps
-  float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  // ---- S = Q K^T  (R x R: MT m-tiles x 2 MT n-tiles of 8 keys), k-dim = 64 in 4 steps
+  float sc[MT][2 * MT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int n = 0; n < 2 * MT; ++n) sc[mt][n][0] = sc[mt][n][1] = sc[mt][n][2] = sc[mt][n][3] = 0.f;
   {
     // ldmatrix.x4 address pattern: lanes 0-15 -> rows 0-15 of the left 8 columns, lanes 16-31 -> the right 8 columns
     const uint32_t qa = smem_u32(&T[0][lane & 15][(lane >> 4) * 8]);
@@ -235,83 +242,111 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, __nv_bfloa
     const uint32_t ka = smem_u32(&T[1][(lane & 7) + ((lane >> 4) << 3)][((lane >> 3) & 1) * 8]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      uint32_t a[4], b[4];
-      ldmatrix_x4(a, qa + k * 32);
-      ldmatrix_x4(b, ka + k * 32);
-      mma_bf16_16816(sc[0], a, b[0], b[1]);
-      mma_bf16_16816(sc[1], a, b[2], b[3]);
+      uint32_t a[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) ldmatrix_x4(a[mt], qa + mt * 16 * SA_PITCH * 2 + k * 32);
+#pragma unroll
+      for (int kt = 0; kt < MT; ++kt) {   // 16 keys per ldmatrix.x4
+        uint32_t b[4];
+        ldmatrix_x4(b, ka + kt * 16 * SA_PITCH * 2 + k * 32);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(sc[mt][2 * kt], a[mt], b[0], b[1]);
+          mma_bf16_16816(sc[mt][2 * kt + 1], a[mt], b[2], b[3]);
+        }
+      }
     }
   }
-  // ---- softmax over the L valid keys (rows g and g + 8 of the accumulator; a row lives in one quad)
-  float mx0 = -INFINITY, mx1 = -INFINITY;
-  const int rs0 = g / L, rs1 = (g + 8) / L;   // which sequence of the tile rows g and g + 8 belong to
+  // ---- softmax over the keys of the query's own sequence (rows g and g + 8 of each m-tile; a row lives in one quad)
+  uint32_t pa[MT][MT][4];   // P as the A operand of O = P V: accumulator layout == A-fragment layout
+  float inv[MT][2];
 #pragma unroll
-  for (int n = 0; n < 2; ++n) {
+  for (int mt = 0; mt < MT; ++mt) {
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+    const int rs0 = (mt * 16 + g) / L, rs1 = (mt * 16 + g + 8) / L;   // which sequence of the tile the rows belong to
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int c = n * 8 + 2 * t + e;         // key column: only keys of the query's own sequence count
-      const int cs = c / L;
-      sc[n][e] = (c < rows && cs == rs0) ? sc[n][e] * scale_log2 : -INFINITY;
-      sc[n][2 + e] = (c < rows && cs == rs1) ? sc[n][2 + e] * scale_log2 : -INFINITY;
-      mx0 = fmaxf(mx0, sc[n][e]);
-      mx1 = fmaxf(mx1, sc[n][2 + e]);
+    for (int n = 0; n < 2 * MT; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = n * 8 + 2 * t + e;         // key column: only keys of the query's own sequence count
+        const int cs = c / L;
+        sc[mt][n][e] = (c < rows && cs == rs0) ? sc[mt][n][e] * scale_log2 : -INFINITY;
+        sc[mt][n][2 + e] = (c < rows && cs == rs1) ? sc[mt][n][2 + e] * scale_log2 : -INFINITY;
+        mx0 = fmaxf(mx0, sc[mt][n][e]);
+        mx1 = fmaxf(mx1, sc[mt][n][2 + e]);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    mx0 = (mx0 == -INFINITY) ? 0.f : mx0;       // padding rows: no valid key
+    mx1 = (mx1 == -INFINITY) ? 0.f : mx1;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 2 * MT; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sc[mt][n][e] = exp2f(sc[mt][n][e] - mx0);
+        sc[mt][n][2 + e] = exp2f(sc[mt][n][2 + e] - mx1);
+        l0 += sc[mt][n][e];
+        l1 += sc[mt][n][2 + e];
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    inv[mt][0] = 1.f / l0;
+    inv[mt][1] = 1.f / l1;
+#pragma unroll
+    for (int kt = 0; kt < MT; ++kt) {
+      pa[mt][kt][0] = pack_bf16x2(sc[mt][2 * kt][0], sc[mt][2 * kt][1]);
+      pa[mt][kt][1] = pack_bf16x2(sc[mt][2 * kt][2], sc[mt][2 * kt][3]);
+      pa[mt][kt][2] = pack_bf16x2(sc[mt][2 * kt + 1][0], sc[mt][2 * kt + 1][1]);
+      pa[mt][kt][3] = pack_bf16x2(sc[mt][2 * kt + 1][2], sc[mt][2 * kt + 1][3]);
     }
   }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  mx0 = (mx0 == -INFINITY) ? 0.f : mx0;       // padding rows: no valid key
-  mx1 = (mx1 == -INFINITY) ? 0.f : mx1;
-  float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-  for (int n = 0; n < 2; ++n) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      sc[n][e] = exp2f(sc[n][e] - mx0);
-      sc[n][2 + e] = exp2f(sc[n][2 + e] - mx1);
-      l0 += sc[n][e];
-      l1 += sc[n][2 + e];
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  // P as the A operand of O = P V (k = 16 keys): accumulator layout == A-fragment layout
-  uint32_t pa[4];
-  pa[0] = pack_bf16x2(sc[0][0], sc[0][1]);
-  pa[1] = pack_bf16x2(sc[0][2], sc[0][3]);
-  pa[2] = pack_bf16x2(sc[1][0], sc[1][1]);
-  pa[3] = pack_bf16x2(sc[1][2], sc[1][3]);
   // ---- O = P V : 8 n-tiles of 8 head-dims; V[key][d] is the row-major [k][n] operand -> ldmatrix.trans
-  float o[8][4];
+  float o[MT][8][4];
 #pragma unroll
-  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) o[mt][n][0] = o[mt][n][1] = o[mt][n][2] = o[mt][n][3] = 0.f;
   {
     // matrices: (keys 0-7, d 0-7), (keys 8-15, d 0-7), (keys 0-7, d 8-15), (keys 8-15, d 8-15)
     const uint32_t va = smem_u32(&T[2][(lane & 7) + (((lane >> 3) & 1) << 3)][(lane >> 4) * 8]);
 #pragma unroll
-    for (int n2 = 0; n2 < 4; ++n2) {
-      uint32_t b[4];
-      ldmatrix_x4_trans(b, va + n2 * 32);
-      mma_bf16_16816(o[2 * n2], pa, b[0], b[1]);
-      mma_bf16_16816(o[2 * n2 + 1], pa, b[2], b[3]);
+    for (int kt = 0; kt < MT; ++kt) {
+#pragma unroll
+      for (int n2 = 0; n2 < 4; ++n2) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, va + kt * 16 * SA_PITCH * 2 + n2 * 32);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(o[mt][2 * n2], pa[mt][kt], b[0], b[1]);
+          mma_bf16_16816(o[mt][2 * n2 + 1], pa[mt][kt], b[2], b[3]);
+        }
+      }
     }
   }
-  // ---- normalise, stage through the (now dead) q tile, store L rows with 16-byte accesses
-  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  // ---- normalise, stage through the (now dead) q tile, store the valid rows with 16-byte accesses
   __syncwarp();
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    *reinterpret_cast<uint32_t*>(&T[0][g][n * 8 + 2 * t]) = pack_bf16x2(o[n][0] * i0, o[n][1] * i0);
-    *reinterpret_cast<uint32_t*>(&T[0][g + 8][n * 8 + 2 * t]) = pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      *reinterpret_cast<uint32_t*>(&T[0][mt * 16 + g][n * 8 + 2 * t]) =
+          pack_bf16x2(o[mt][n][0] * inv[mt][0], o[mt][n][1] * inv[mt][0]);
+      *reinterpret_cast<uint32_t*>(&T[0][mt * 16 + g + 8][n * 8 + 2 * t]) =
+          pack_bf16x2(o[mt][n][2] * inv[mt][1], o[mt][n][3] * inv[mt][1]);
+    }
   }
   __syncwarp();
   {
     const int ch = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 4 * MT; ++i) {
       const int r = (lane >> 3) + 4 * i;
       if (gr[i] >= 0)
         *reinterpret_cast<uint4*>(out + size_t(gr[i]) * ldo + h * 64 + ch * 8) =
@@ -363,13 +398,20 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
 
 extern "C" int bya_small_attention(void* stream, const void* qkv, int ld, void* out, int ldo, int n_seq, int seq_len,
                                    int heads, int inner, long long outer_stride, long long tok_stride, float scale) {
-  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || seq_len > 16 || heads <= 0 || inner <= 0) return BYA_ERR_SHAPE;
+  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || seq_len > 32 || heads <= 0 || inner <= 0) return BYA_ERR_SHAPE;
   if (ld % 8 || ldo % 8) return BYA_ERR_ALIGN;
-  const int spw = 16 / seq_len;
+  const int mt = seq_len <= 16 ? 1 : 2;          // 97-frame clips have 25 latent frames: two 16-row tiles
+  const int spw = 16 * mt / seq_len;
+  const int nw = SA_WARPS / mt;
   const long long units = (long long)((n_seq + spw - 1) / spw) * heads;
-  const int blocks = int((units + SA_WARPS - 1) / SA_WARPS);
-  small_attention_kernel<<<blocks, SA_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq, seq_len, heads, inner, outer_stride, tok_stride,
-      scale * 1.4426950408889634f);
+  const int blocks = int((units + nw - 1) / nw);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float sl2 = scale * 1.4426950408889634f;
+  if (mt == 1)
+    small_attention_kernel<1><<<blocks, nw * 32, 0, st>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq,
+                                                          seq_len, heads, inner, outer_stride, tok_stride, sl2);
+  else
+    small_attention_kernel<2><<<blocks, nw * 32, 0, st>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)out, ldo, n_seq,
+                                                          seq_len, heads, inner, outer_stride, tok_stride, sl2);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }

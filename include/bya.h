@@ -106,7 +106,7 @@ int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* K, const vo
                    int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames, float scale,
                    long long tok_begin, long long total_tokens);
 
-/* Router temporal / multi-ID self-attention (router.py:478-488): n_seq sequences of seq_len rows of the
+/* Router temporal / multi-ID self-attention (router.py:478-488): n_seq sequences of seq_len <= 32 rows of the
  * [rows, 3*heads*64] qkv matrix, rows of one sequence `tok_stride` apart, first row (s/inner)*outer_stride + s%inner. */
 int bya_small_attention(void* stream, const void* qkv, int ld, void* out, int ldo, int n_seq, int seq_len, int heads,
                         int inner, long long outer_stride, long long tok_stride, float scale);

@@ -1,6 +1,7 @@
 """-m gpu: each sm_100a kernel through the C ABI vs a plain torch fp32 reference of the same op (tolerances stated
 per test: bf16 outputs, fp32 accumulation), incl. ragged / tail shapes; mask path bit-exact vs the C oracle and the
 reference-produced goldens."""
+import math
 import os
 
 import numpy as np
@@ -126,6 +127,39 @@ def test_attention_d64(ops, batch, seq, heads, qs):
     assert rel(out, ref) < 2e-2
 
 
+@pytest.mark.parametrize("batch,seq,heads", [(1, 128, 1), (1, 1000, 3), (2, 1350, 8), (1, 1474, 48), (3, 77, 2)])
+def test_attention_d64_bounded(ops, batch, seq, heads):
+    """Max-free kernel (`bya_attention_d64_bounded`): q carries scale*log2(e), |q.k| <= bound.  Reference: the same
+    softmax in fp32 (softmax_2(s) = softmax(s ln 2)).  Rows/keys past the sequence end and batch boundaries are covered
+    by the non-multiple-of-128 lengths."""
+    torch.manual_seed(3)
+    D = heads * 64
+    x = torch.randn(batch * seq, 3 * heads, 64, device=dev)
+    x[:, :2 * heads] = F.layer_norm(x[:, :2 * heads], (64,)) * 1.3            # |q| = |k| = 8 * 1.3 like qk-LayerNorm
+    x[:, :heads] *= 0.125 * 1.4426950408889634
+    qkv = x.reshape(batch * seq, 3 * D).bfloat16()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    bound = 1.02 * (8 * 1.3) ** 2 * 0.125 * 1.4426950408889634
+    out = torch.zeros(batch * seq, D, device=dev, dtype=torch.bfloat16)
+    ops.attention_d64(q, k, v, out, batch, seq, heads, score_bound_log2=bound)
+    hv = lambda t: t.reshape(batch, seq, heads, 64).transpose(1, 2).float()
+    ref = F.scaled_dot_product_attention(hv(q), hv(k), hv(v), scale=math.log(2.0)).transpose(1, 2).reshape(batch * seq, D)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < TOL
+    # the general kernel on the same (pre-scaled) inputs agrees: scale = 1 / log2(e) undoes the folded log2(e)
+    out2 = torch.zeros_like(out)
+    ops.attention_d64(q, k, v, out2, batch, seq, heads, scale=math.log(2.0))
+    assert rel(out2, out) < TOL
+
+
+def test_attention_d64_bounded_rejects_bad_bound(ops):
+    qkv = rnd(128, 192)
+    out = torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)
+    for bad in (0.0, -1.0, 64.5, float("nan")):
+        with pytest.raises(RuntimeError):
+            ops.attention_d64(qkv[:, :64], qkv[:, 64:128], qkv[:, 128:], out, 1, 128, 1, score_bound_log2=bad)
+
+
 @pytest.mark.parametrize("dim", [512, 768, 1024, 2048, 3072])
 def test_layernorm_modulate(ops, dim):
     torch.manual_seed(6)
@@ -219,6 +253,18 @@ def test_router_small_attention_and_head(ops):
     q, k, v = (x[:, :, i].permute(1, 2, 0, 3) for i in range(3))  # [Nv,H,C,64]
     ref = F.scaled_dot_product_attention(q, k, v).permute(2, 0, 1, 3).reshape(C * Nv, 512)
     assert rel(out, ref) < TOL
+    # other sequence lengths: 3 characters, a full 16-row tile, 25 latent frames (97-frame clips: two 16-row tiles)
+    for L, hw2 in ((3, 50), (16, 7), (17, 5), (25, 11), (32, 3)):
+        n = L * hw2
+        qkv2 = rnd(n, 1536)
+        out2 = torch.zeros(n, 512, device=dev, dtype=torch.bfloat16)
+        ops.small_attention(qkv2, out2, hw2, L, H, hw2, 0, hw2)   # sequences of L rows, hw2 apart
+        x = qkv2.float().view(L, hw2, 3, H, 64)
+        q, k, v = (x[:, :, i].permute(1, 2, 0, 3) for i in range(3))  # [hw2,H,L,64]
+        ref = F.scaled_dot_product_attention(q, k, v).permute(2, 0, 1, 3).reshape(n, 512)
+        assert rel(out2, ref) < TOL, L
+    with pytest.raises(RuntimeError):
+        ops.small_attention(rnd(33 * 2, 1536), torch.zeros(66, 512, device=dev, dtype=torch.bfloat16), 2, 33, H, 2, 0, 2)
     xh, w, b = rnd(C * Nv, 512), rnd(512, s=0.1), rnd(1)
     r = torch.empty(Nv, C, device=dev)
     ops.router_head(xh, w, b, r, Nv, C)
