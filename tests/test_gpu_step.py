@@ -135,6 +135,21 @@ def test_three_characters_and_per_frame_masks(built):
     assert cos(m(**soft)[0], restated.step(sd, cfg, **oracle_inputs(soft))) >= 0.999
 
 
+def test_long_clip_25_latent_frames(built):
+    """Config 5 geometry (97 frames -> 25 latent frames; beyond the reference, which raises above 49 frames —
+    transformer.py:638-643): the generalised oracle on a reduced grid.  Exercises the two-tile temporal attention."""
+    from bya_b200.synth import CONFIGS, make_inputs
+    from oracle import restated
+
+    cfg = dataclasses.replace(CONFIGS["c1"], frames=25, grid_h=4, grid_w=6)
+    m = build(cfg)
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    inp = make_inputs(cfg, 11, device="cuda", dtype=torch.bfloat16)
+    out = m(**inp)[0]
+    assert out.shape[1] == 25
+    assert cos(out, restated.step(sd, cfg, **oracle_inputs(inp))) >= 0.999
+
+
 def test_full_grid_one_layer_vs_reference_golden(built):
     """Full 13x30x45 grid (17 776 tokens), 1 layer, forced masks: golden produced by the UNMODIFIED reference."""
     from bya_b200.synth import PathConfig, make_inputs
