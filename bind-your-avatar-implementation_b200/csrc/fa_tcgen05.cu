@@ -42,13 +42,19 @@ namespace bya {
 constexpr int FA_D = 64;
 constexpr int FA_BM = 128;         // query rows per tile (2 tiles per CTA)
 constexpr int FA_BN = 128;         // keys per KV tile
-constexpr int FA_STAGES = 4;       // K ring depth == V ring depth
+__host__ __device__ constexpr int fa_stages(int qt) { return qt == 1 ? 3 : 4; }   // K ring depth == V ring depth
 constexpr int FA_TILE_BYTES = FA_BM * FA_D * 2;  // 16 KB
-constexpr int fa_threads(int nt) { return 256 * nt + 128; }   // nt softmax threads per query row + one issuing warpgroup
-constexpr int FA_SMEM = (2 + 2 * FA_STAGES) * FA_TILE_BYTES + 512 + 1024;
+// qt query tiles per CTA, nt softmax threads per query row, + one issuing warpgroup
+__host__ __device__ constexpr int fa_threads(int qt, int nt) { return 128 * qt * nt + 128; }
+// V ring depth: with two CTAs per SM (qt == 1) each may use at most ~113 KB: 1 Q + 3 K + 2 V tiles
+__host__ __device__ constexpr int fa_vstages(int qt) { return qt == 1 ? 2 : 4; }
+__host__ __device__ constexpr int fa_smem(int qt) {
+  return (qt + fa_stages(qt) + fa_vstages(qt)) * FA_TILE_BYTES + 512 + 1024;
+}
 
 struct FaArgs {
   int seq;        // rows per batch element (queries == keys)
+  int seq_stride; // first row of batch element b is b * seq_stride (>= seq: padding rows between sequences are skipped)
   int heads;
   int batch;
   int ldo;        // row stride of O in elements
@@ -153,22 +159,28 @@ BYA_DEVICE void ex2_poly2(float& y0, float& y1, float x0, float x1) {
 // nothing but the final row sum) doubles the warps per SM sub-partition.  Measured: no gain (1066 vs 1055 TFLOP/s) —
 // the exp phase is bound by dispatch/pipe occupancy (every f32x2 / F2FP instruction holds its pipe for 2 cycles), not by
 // latency hiding — so NT = 1 is the default; the variant is kept for the next round of tuning.
-template <int POLY16, bool BOUNDED, int NT>
-__global__ void __launch_bounds__(fa_threads(NT), 1)
+// QT: 128-row query tiles per CTA.  QT = 2: one CTA per SM, the two tiles ping-pong on the tensor pipe but their softmax
+// warps fall into lock-step (the MMA warp serves them in order, the arbiter prefers the higher warp id), so MUFU idles
+// while BOTH load / wait / store.  QT = 1: two independent CTAs per SM (256 TMEM columns and half the registers each)
+// whose phases drift apart freely.
+template <int POLY16, bool BOUNDED, int NT, int QT>
+__global__ void __launch_bounds__(fa_threads(QT, NT), QT == 1 ? 2 : 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const __grid_constant__ CUtensorMap tmap_v, const FaArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // [2][16 KB]
-  uint8_t* sK = sQ + 2 * FA_TILE_BYTES;                 // [STAGES][16 KB]
+  constexpr int FA_STAGES = fa_stages(QT);
+  constexpr int FA_VSTAGES = fa_vstages(QT);
+  uint8_t* sQ = smem;                                   // [QT][16 KB]
+  uint8_t* sK = sQ + QT * FA_TILE_BYTES;                // [STAGES][16 KB]
   uint8_t* sV = sK + FA_STAGES * FA_TILE_BYTES;         // [STAGES][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_STAGES * FA_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FA_VSTAGES * FA_TILE_BYTES);
   uint64_t* q_full = bars;                    // [1]
   uint64_t* k_full = q_full + 1;              // [STAGES]
   uint64_t* k_empty = k_full + FA_STAGES;     // [STAGES]
   uint64_t* v_full = k_empty + FA_STAGES;     // [STAGES]
-  uint64_t* v_empty = v_full + FA_STAGES;     // [STAGES]
-  uint64_t* s_full = v_empty + FA_STAGES;     // [2]  S_t(j) = Q_t K(j)^T landed in TMEM
+  uint64_t* v_empty = v_full + FA_VSTAGES;    // [VSTAGES]
+  uint64_t* s_full = v_empty + FA_VSTAGES;     // [2]  S_t(j) = Q_t K(j)^T landed in TMEM
   uint64_t* s_free = s_full + 2;              // [2]  S_t(j) is in the softmax registers: S_t may be overwritten
   uint64_t* p_full = s_free + 2;              // [2]  P_t(j) written to TMEM
   uint64_t* pv_done = p_full + 2;             // [2]  O_t += P_t(j) V(j) complete: P_t free, O_t stable
@@ -177,12 +189,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform: role/TMEM addresses
   const int lane = threadIdx.x & 31;                                // stay in uniform registers
   const int qblk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-  const int row_base = b * p.seq;               // first row of this batch element in the [rows, ld] matrices
-  const int q0 = qblk * (2 * FA_BM);            // first query row (within the batch element)
+  const int row_base = b * p.seq_stride;        // first row of this batch element in the [rows, ld] matrices
+  const int q0 = qblk * (QT * FA_BM);           // first query row (within the batch element)
   const int n_kv = (p.seq + FA_BN - 1) / FA_BN;
   const int col = head * FA_D;
 
-  constexpr int W0 = 8 * NT;   // first warp of the issuing warpgroup
+  constexpr int W0 = 4 * QT * NT;   // first warp of the issuing warpgroup
   if (warp == W0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
@@ -193,10 +205,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     for (int s = 0; s < FA_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < FA_VSTAGES; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < QT; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&s_free[t], 4 * NT);    // one arrive per softmax warp
       mbar_init(&p_full[t], 4 * NT);
@@ -204,21 +218,23 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == W0 + 2) tmem_alloc<512>(tmem_slot);
+  constexpr int kTmemCols = 256 * QT;
+  if (warp == W0 + 2) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kColS = 0, kColP = 256, kColO = 384;
+  constexpr uint32_t kColS = 0, kColP = 128 * QT, kColO = 192 * QT;
 
   if (warp >= W0) {
-    setmaxnreg_dec<(NT == 1 ? 56 : 40)>();
+    // register pool of the launch: (65536 / CTAs per SM / threads) rounded down to 8 per thread
+    setmaxnreg_dec<((NT == 1 && QT == 2) ? 56 : 40)>();
     if (warp == W0) {
       // ---------------------------------------------------------------- TMA producer (one elected thread)
       if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, 2 * FA_TILE_BYTES);
+        mbar_arrive_expect_tx(q_full, QT * FA_TILE_BYTES);
         tma_load_2d(sQ, &tmap_q, q_full, col, row_base + q0, kEvictFirst);
-        tma_load_2d(sQ + FA_TILE_BYTES, &tmap_q, q_full, col, row_base + q0 + FA_BM, kEvictFirst);
+        if (QT == 2) tma_load_2d(sQ + FA_TILE_BYTES, &tmap_q, q_full, col, row_base + q0 + FA_BM, kEvictFirst);
         // order: K(0), then K(j+1), V(j): K runs one tile ahead because S(j+1) is computed before O += P(j) V(j)
         mbar_arrive_expect_tx(&k_full[0], FA_TILE_BYTES);
         tma_load_2d(sK, &tmap_k, &k_full[0], col, row_base, kEvictLast);
@@ -234,7 +250,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mbar_wait(&v_empty[vs], vph ^ 1);
           mbar_arrive_expect_tx(&v_full[vs], FA_TILE_BYTES);
           tma_load_2d(sV + vs * FA_TILE_BYTES, &tmap_v, &v_full[vs], col, row_base + j * FA_BN, kEvictLast);
-          if (++vs == FA_STAGES) { vs = 0; vph ^= 1; }
+          if (++vs == FA_VSTAGES) { vs = 0; vph ^= 1; }
         }
       }
     } else if (warp == W0 + 1) {
@@ -244,7 +260,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, FA_D, 0, 1);  // B = V is MN-major (d contiguous)
       const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-      const uint64_t dq1 = make_smem_desc_sw128(smem_u32(sQ + FA_TILE_BYTES), 16, 1024);
+      const uint64_t dq1 = make_smem_desc_sw128(smem_u32(sQ + (QT - 1) * FA_TILE_BYTES), 16, 1024);
       const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV), 1024, 1024);
       constexpr uint64_t kStageStep = FA_TILE_BYTES >> 4;   // descriptor address field is in 16 B units
@@ -259,9 +275,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < FA_D / 16; ++k) umma_ss(tS0, dq0 + uint64_t(2 * k), dk0 + uint64_t(2 * k), idesc_qk, k != 0);
         umma_commit(&s_full[0]);
+        if (QT == 2) {
 #pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k) umma_ss(tS1, dq1 + uint64_t(2 * k), dk0 + uint64_t(2 * k), idesc_qk, k != 0);
-        umma_commit(&s_full[1]);
+          for (int k = 0; k < FA_D / 16; ++k) umma_ss(tS1, dq1 + uint64_t(2 * k), dk0 + uint64_t(2 * k), idesc_qk, k != 0);
+          umma_commit(&s_full[1]);
+        }
         umma_commit(&k_empty[0]);
       }
       __syncwarp();
@@ -281,19 +299,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             for (int k = 0; k < FA_D / 16; ++k)
               umma_ss(tS0, dq0 + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk, k != 0);
             umma_commit(&s_full[0]);
+            if (QT == 1) umma_commit(&k_empty[ks]);
           }
           __syncwarp();
-          mbar_wait(&s_free[1], jp);
-          FA_TRACE(9, j);
-          tc_fence_after();
-          if (elect_one()) {
+          if (QT == 2) {
+            mbar_wait(&s_free[1], jp);
+            FA_TRACE(9, j);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < FA_D / 16; ++k)
-              umma_ss(tS1, dq1 + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk, k != 0);
-            umma_commit(&s_full[1]);
-            umma_commit(&k_empty[ks]);
+              for (int k = 0; k < FA_D / 16; ++k)
+                umma_ss(tS1, dq1 + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk, k != 0);
+              umma_commit(&s_full[1]);
+              umma_commit(&k_empty[ks]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
           if (++ks == FA_STAGES) { ks = 0; kph ^= 1; }
         }
         // O_t += P_t(j) V(j)
@@ -308,28 +329,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           for (int k = 0; k < FA_BN / 16; ++k)
             umma_ts(tO0, tP0 + k * 8, dv + uint64_t(128 * k), idesc_pv, acc | (k != 0));
           umma_commit(&pv_done[0]);
+          if (QT == 1) umma_commit(&v_empty[vs]);
         }
         __syncwarp();
-        mbar_wait(&p_full[1], jp);
-        FA_TRACE(11, j);
-        tc_fence_after();
-        if (elect_one()) {
+        if (QT == 2) {
+          mbar_wait(&p_full[1], jp);
+          FA_TRACE(11, j);
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < FA_BN / 16; ++k)
-            umma_ts(tO1, tP1 + k * 8, dv + uint64_t(128 * k), idesc_pv, acc | (k != 0));
-          umma_commit(&pv_done[1]);
-          umma_commit(&v_empty[vs]);
+            for (int k = 0; k < FA_BN / 16; ++k)
+              umma_ts(tO1, tP1 + k * 8, dv + uint64_t(128 * k), idesc_pv, acc | (k != 0));
+            umma_commit(&pv_done[1]);
+            umma_commit(&v_empty[vs]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
         FA_TRACE(12, j);
-        if (++vs == FA_STAGES) { vs = 0; vph ^= 1; }
+        if (++vs == FA_VSTAGES) { vs = 0; vph ^= 1; }
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax warps (one thread per query row)
     static_assert(NT == 1 || BOUNDED, "two threads per row need the max-free softmax");
     // register pool of the launch: 65536 / threads rounded down to 8 -> 168 (NT=1) / 96 (NT=2) per thread
-    setmaxnreg_inc<(NT == 1 ? 224 : 104)>();
+    setmaxnreg_inc<(QT == 1 ? 216 : (NT == 1 ? 224 : 104))>();
     constexpr int NC = FA_BN / NT;   // score columns per thread
     constexpr int OC = FA_D / NT;    // O columns per thread (final normalisation + store)
     const int t = (warp / (4 * NT));   // query tile 0 / 1
@@ -535,44 +559,62 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   __syncthreads();
   if (warp == W0 + 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
 using FaKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const FaArgs);
 
 // Tuning knobs, read once: BYA_FA_POLY16 / BYA_FA_POLY16_BOUNDED (0, 4, 8, 12: exponentials per 16 moved from MUFU
-// to the FMA pipe) and BYA_FA_NT (bounded kernel only: 1 or 2 softmax threads per query row).
+// to the FMA pipe), BYA_FA_NT (bounded kernel only: 1 or 2 softmax threads per query row), BYA_FA_QT / BYA_FA_QT_BOUNDED
+// (force 1 or 2 query tiles per CTA; default: by sequence length, see fa_launch).
 template <bool BOUNDED>
-static FaKernel fa_pick_kernel(int* threads) {
+static FaKernel fa_pick_kernel(int qt, int* threads) {
   int poly = 4, nt = 1;
   if (const char* e = std::getenv(BOUNDED ? "BYA_FA_POLY16_BOUNDED" : "BYA_FA_POLY16")) poly = std::atoi(e);
   if (const char* e = std::getenv("BYA_FA_NT")) nt = (BOUNDED && std::atoi(e) == 2) ? 2 : 1;
-  *threads = fa_threads(nt);
+  if (qt == 1) nt = 1;
+  *threads = fa_threads(qt, nt);
+  if (qt == 1) {
+    switch (poly) {
+      case 0: return fa_fwd_kernel<0, BOUNDED, 1, 1>;
+      case 8: return fa_fwd_kernel<8, BOUNDED, 1, 1>;
+      default: return fa_fwd_kernel<4, BOUNDED, 1, 1>;
+    }
+  }
   if constexpr (BOUNDED) {
     if (nt == 2) {
       switch (poly) {
-        case 0: return fa_fwd_kernel<0, true, 2>;
-        case 4: return fa_fwd_kernel<4, true, 2>;
-        case 12: return fa_fwd_kernel<12, true, 2>;
-        default: return fa_fwd_kernel<8, true, 2>;
+        case 0: return fa_fwd_kernel<0, true, 2, 2>;
+        case 4: return fa_fwd_kernel<4, true, 2, 2>;
+        case 12: return fa_fwd_kernel<12, true, 2, 2>;
+        default: return fa_fwd_kernel<8, true, 2, 2>;
       }
     }
   }
   switch (poly) {
-    case 0: return fa_fwd_kernel<0, BOUNDED, 1>;
-    case 4: return fa_fwd_kernel<4, BOUNDED, 1>;
-    case 12: return fa_fwd_kernel<12, BOUNDED, 1>;
-    default: return fa_fwd_kernel<8, BOUNDED, 1>;
+    case 0: return fa_fwd_kernel<0, BOUNDED, 1, 2>;
+    case 4: return fa_fwd_kernel<4, BOUNDED, 1, 2>;
+    case 12: return fa_fwd_kernel<12, BOUNDED, 1, 2>;
+    default: return fa_fwd_kernel<8, BOUNDED, 1, 2>;
   }
 }
 
 template <bool BOUNDED>
 static int fa_launch(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo, int batch,
-                     int seq, int heads, float scale) {
-  if (!q || !k || !v || !out || batch <= 0 || seq <= 0 || heads <= 0) return BYA_ERR_SHAPE;
+                     int seq, int seq_stride, int heads, float scale) {
+  if (!q || !k || !v || !out || batch <= 0 || seq <= 0 || heads <= 0 || seq_stride < seq) return BYA_ERR_SHAPE;
   if (ld % 8 || ldo % 8 || ld < heads * FA_D || ldo < heads * FA_D) return BYA_ERR_ALIGN;
-  const uint64_t rows = uint64_t(batch) * seq;
+  const uint64_t rows = uint64_t(batch - 1) * seq_stride + seq;
+  // Short sequences (the router's 1 350-token frames): one 128-row query tile per CTA and two CTAs per SM — a CTA only
+  // lives for ~11 KV tiles, so its fill / drain overlaps the other CTA's work (measured 152 vs 175 us per call).  Long
+  // sequences: two tiles per CTA sharing every K/V tile (947 vs 890 TFLOP/s at 17 776 tokens).
+  static int forced_qt = -1;
+  if (forced_qt < 0) {
+    const char* e = std::getenv(BOUNDED ? "BYA_FA_QT_BOUNDED" : "BYA_FA_QT");
+    forced_qt = e ? (std::atoi(e) == 1 ? 1 : 2) : 0;
+  }
+  const int qt = forced_qt ? forced_qt : (seq < 4096 ? 1 : 2);
   CUtensorMap tq, tk, tv;
   int rc = bya_host::encode_tmap_bf16(&tq, q, uint64_t(heads) * FA_D, rows, uint64_t(ld) * 2, FA_D, FA_BM);
   if (rc) return rc;
@@ -580,16 +622,17 @@ static int fa_launch(void* stream, const void* q, const void* k, const void* v, 
   if (rc) return rc;
   rc = bya_host::encode_tmap_bf16(&tv, v, uint64_t(heads) * FA_D, rows, uint64_t(ld) * 2, FA_D, FA_BN);
   if (rc) return rc;
-  static FaKernel kern = nullptr;
-  static int threads = 0;
-  if (!kern) {
-    FaKernel kk = fa_pick_kernel<BOUNDED>(&threads);
-    if (cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess)
+  static FaKernel kern[3] = {nullptr, nullptr, nullptr};
+  static int threads[3] = {0, 0, 0};
+  if (!kern[qt]) {
+    FaKernel kk = fa_pick_kernel<BOUNDED>(qt, &threads[qt]);
+    if (cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, fa_smem(qt)) != cudaSuccess)
       return BYA_ERR_CUDA;
-    kern = kk;
+    kern[qt] = kk;
   }
   FaArgs a;
   a.seq = seq;
+  a.seq_stride = seq_stride;
   a.heads = heads;
   a.batch = batch;
   a.ldo = ldo;
@@ -597,8 +640,8 @@ static int fa_launch(void* stream, const void* q, const void* k, const void* v, 
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.trace = nullptr;
   if (const char* e = std::getenv("BYA_FA_TRACE")) a.trace = reinterpret_cast<long long*>(std::strtoull(e, nullptr, 0));
-  dim3 grid((seq + 2 * FA_BM - 1) / (2 * FA_BM), heads, batch);
-  kern<<<grid, threads, FA_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
+  dim3 grid((seq + qt * FA_BM - 1) / (qt * FA_BM), heads, batch);
+  kern[qt]<<<grid, threads[qt], fa_smem(qt), reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }
 
@@ -606,11 +649,16 @@ static int fa_launch(void* stream, const void* q, const void* k, const void* v, 
 
 extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo,
                                  int batch, int seq, int heads, float scale) {
-  return bya::fa_launch<false>(stream, q, k, v, ld, out, ldo, batch, seq, heads, scale);
+  return bya::fa_launch<false>(stream, q, k, v, ld, out, ldo, batch, seq, seq, heads, scale);
+}
+
+extern "C" int bya_attention_d64_strided(void* stream, const void* q, const void* k, const void* v, int ld, void* out,
+                                         int ldo, int batch, int seq, int seq_stride, int heads, float scale) {
+  return bya::fa_launch<false>(stream, q, k, v, ld, out, ldo, batch, seq, seq_stride, heads, scale);
 }
 
 extern "C" int bya_attention_d64_bounded(void* stream, const void* q, const void* k, const void* v, int ld, void* out,
                                          int ldo, int batch, int seq, int heads, float score_bound_log2) {
   if (!(score_bound_log2 > 0.f) || score_bound_log2 > 64.f) return BYA_ERR_SHAPE;   // also rejects NaN
-  return bya::fa_launch<true>(stream, q, k, v, ld, out, ldo, batch, seq, heads, 1.0f);
+  return bya::fa_launch<true>(stream, q, k, v, ld, out, ldo, batch, seq, seq, heads, 1.0f);
 }

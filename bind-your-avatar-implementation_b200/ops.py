@@ -84,14 +84,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
 
 
 def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, batch: int, seq: int,
-                  heads: int, scale: float = 0.125, tag=None, score_bound_log2: Optional[float] = None) -> torch.Tensor:
+                  heads: int, scale: float = 0.125, tag=None, score_bound_log2: Optional[float] = None,
+                  seq_stride: Optional[int] = None) -> torch.Tensor:
     """q/k/v/out: [batch*seq, heads*64] column-slice views (shared row stride for q,k,v) of bf16 matrices.
     With `score_bound_log2` (<= 64): q is pre-scaled so that q.k is in log2 units and |q.k| <= the bound
     (`bya_attention_d64_bounded`); `scale` is then ignored."""
     global LAUNCHES
+    stride = seq if seq_stride is None else seq_stride
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _bf16_2d(t, n)
-        if t.shape[0] != batch * seq or t.shape[1] != heads * 64:
+        if t.shape[0] < (batch - 1) * stride + seq or t.shape[1] != heads * 64 or (seq_stride is None and t.shape[0] != batch * seq):
             raise RuntimeError(f"bya_b200.attention_d64: {n} has shape {tuple(t.shape)}")
     if not (q.stride(0) == k.stride(0) == v.stride(0)):
         raise RuntimeError("bya_b200.attention_d64: q, k, v must share a row stride")
@@ -99,6 +101,9 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.
     if score_bound_log2 is not None:
         rc = lib().bya_attention_d64_bounded(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
                                              batch, seq, heads, ctypes.c_float(score_bound_log2))
+    elif seq_stride is not None:
+        rc = lib().bya_attention_d64_strided(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
+                                             batch, seq, seq_stride, heads, ctypes.c_float(scale))
     else:
         rc = lib().bya_attention_d64(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
                                      batch, seq, heads, ctypes.c_float(scale))

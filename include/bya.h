@@ -85,6 +85,10 @@ int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W, int ldw, 
  * inside the router's spatial attention (router.py:474-476). */
 int bya_attention_d64(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo,
                       int batch, int seq, int heads, float scale);
+/* Same, with batch element b starting at row b * seq_stride (seq_stride >= seq; the rows in between are ignored).
+ * Used by the sequence-parallel router, whose frames are padded to a multiple of the group size. */
+int bya_attention_d64_strided(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo,
+                              int batch, int seq, int seq_stride, int heads, float scale);
 /* Same attention for BOUNDED, pre-scaled scores: out = softmax_2(Q_h K_h^T) V_h with softmax_2(s) = 2^s / sum 2^s,
  * i.e. q already carries scale * log2(e) (ByaGemmArgs.q_premul), and the caller guarantees |q.k| <= score_bound_log2
  * <= 64 for every (query, key) pair — true for the joint self-attention because diffusers applies LayerNorm(64) to

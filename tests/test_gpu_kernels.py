@@ -152,6 +152,24 @@ def test_attention_d64_bounded(ops, batch, seq, heads):
     assert rel(out2, out) < TOL
 
 
+def test_attention_d64_strided_batches(ops):
+    """Sequences `seq_stride` rows apart with padding rows in between (sequence-parallel router frames): the padding
+    must neither be attended to nor written."""
+    torch.manual_seed(4)
+    batch, seq, stride, heads = 5, 1350, 1352, 2
+    D = heads * 64
+    qkv = rnd(batch * stride, 3 * D)
+    qkv.view(batch, stride, 3 * D)[:, seq:] = 1e4          # poison the padding rows
+    out = torch.full((batch * stride, D), 7.0, device=dev, dtype=torch.bfloat16)
+    ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, batch, seq, heads, seq_stride=stride)
+    x = qkv.view(batch, stride, 3, heads, 64)[:, :seq].float()
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(batch, seq, D)
+    o = out.view(batch, stride, D)
+    assert rel(o[:, :seq], ref) < 2e-2
+    assert bool((o[:, seq:] == 7.0).all())
+
+
 def test_attention_d64_bounded_rejects_bad_bound(ops):
     qkv = rnd(128, 192)
     out = torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)
