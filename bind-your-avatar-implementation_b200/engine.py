@@ -132,6 +132,95 @@ def run_router(rp: RouterPack, ws: _Workspace, qf: torch.Tensor, kmat: torch.Ten
     return out
 
 
+class RouterShard:
+    """Sequence-parallel layout of the router: rank r owns the spatial positions
+    [r*hwl, (r+1)*hwl) of EVERY (character, frame) — hwl = ceil(hw / P), the last rank's slice is padded with copies of
+    the last real position — so the temporal, multi-ID and row-local parts are local, and only the spatial attention
+    (all positions of one frame) needs an exchange: Ulysses over its 8 heads, q|k|v out / attention output back."""
+
+    def __init__(self, rp: RouterPack, frames: int, hw: int, world: int, rank: int, device):
+        from .sp import qkv_rows_by_destination
+
+        if 8 % world:
+            raise RuntimeError(f"bya_b200: the router's 8 heads are not divisible by the sequence-parallel size {world}")
+        self.P, self.rank, self.frames, self.hw = world, rank, frames, hw
+        self.hwl = (hw + world - 1) // world
+        self.hw_pad = self.hwl * world
+        self.hl = 8 // world                      # spatial-attention heads per rank
+        j = torch.arange(self.hwl, device=device) + rank * self.hwl
+        f = torch.arange(frames, device=device)
+        self.idx = (f[:, None] * hw + j.clamp(max=hw - 1)[None, :]).reshape(-1)    # [F*hwl] global token of local row
+        self.pos = rp.pos.index_select(0, self.idx).contiguous()
+        self.blocks = [dict(w=qkv_rows_by_destination(d["s_qkv_w"], 512, world),
+                            b=qkv_rows_by_destination(d["s_qkv_b"], 512, world)) for d in rp.blocks]
+
+
+def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all: torch.Tensor, kmat: torch.Tensor, layer: int,
+                  chars: int, out: torch.Tensor, group) -> torch.Tensor:
+    """`run_router` sharded over the sequence-parallel group: q_all [Nv,2048] (every rank holds all face queries) ->
+    out [Nv,C] fp32 on every rank.  Same kernels, same per-row arithmetic as the single-GPU router."""
+    import torch.distributed as dist
+
+    C, Fr, P, hwl, hl = chars, rs.frames, rs.P, rs.hwl, rs.hl
+    R = Fr * hwl                 # local (frame, position) rows
+    M = C * R                    # local router rows, ordered (character, frame, local position)
+    CF = C * Fr
+    Ws, Wo = 3 * hl * 64, hl * 64
+    qf = ws.get("rs_qsel", (R, 2048))
+    torch.index_select(q_all, 0, rs.idx, out=qf)
+    rq = ws.get("rs_q", (R, 2048))
+    ops.layernorm_modulate(qf, rq, eps=rp.eps, gamma=rp.nq_w, beta=rp.nq_b)
+    rq2 = ws.get("rs_q2", (R, 2048))
+    ops.gemm(rq, rp.to_q[layer], rq2)
+    sc = ws.get("rs_scores", (R, C * 512))
+    ops.gemm(rq2, kmat, sc)
+    x = ws.get("rs_x", (M, 512))
+    for c in range(C):
+        ops.layernorm_modulate(sc[:, c * 512:(c + 1) * 512], x[c * R:(c + 1) * R], eps=rp.eps, gamma=rp.n_w, beta=rp.n_b,
+                               add=rs.pos)
+    xn = ws.get("rs_xn", (M, 512))
+    qkv = ws.get("rs_qkv", (M, 1536))
+    att = ws.get("rs_att", (M, 512))
+    s_send = ws.get("rs_s_send", (P, M, Ws))          # [dest][local row][q|k|v heads of dest]
+    s_recv = ws.get("rs_s_recv", (P, M, Ws))          # [src][(c,f), src's positions][my heads]
+    s_full = ws.get("rs_s_full", (CF * rs.hw_pad, Ws))   # [(c,f)][all positions (padded)][my heads]
+    s_att = ws.get("rs_s_att", (CF * rs.hw_pad, Wo))
+    o_send = ws.get("rs_o_send", (P, M, Wo))
+    o_recv = ws.get("rs_o_recv", (P, M, Wo))          # [src heads][local row] = K-blocked A of the out-projection
+    for d, dsp in zip(rp.blocks, rs.blocks):
+        # spatial: all H*W tokens of one (character, frame) — heads sharded, positions gathered
+        ops.layernorm_modulate(x, xn, eps=d["n1"][2], gamma=d["n1"][0], beta=d["n1"][1])
+        ops.gemm(xn, dsp["w"], s_send[0], bias=dsp["b"], col_block=Ws, col_block_stride=M * Ws)
+        dist.all_to_all_single(s_recv, s_send, group=group)
+        s_full.view(CF, P, hwl, Ws).copy_(s_recv.view(P, CF, hwl, Ws).permute(1, 0, 2, 3))
+        ops.attention_d64(s_full[:, :Wo], s_full[:, Wo:2 * Wo], s_full[:, 2 * Wo:], s_att, CF, rs.hw, hl,
+                          seq_stride=rs.hw_pad)
+        o_send.view(P, CF, hwl, Wo).copy_(s_att.view(CF, P, hwl, Wo).permute(1, 0, 2, 3))
+        dist.all_to_all_single(o_recv, o_send, group=group)
+        ops.gemm(o_recv[0], d["s_o_w"], x, bias=d["s_o_b"], mode=ops.EPI_RESIDUAL, resid=x, a_kblock=Wo,
+                 a_kblock_stride=M * Wo)
+        # temporal: the F tokens at one (character, local position)
+        ops.layernorm_modulate(x, xn, eps=d["n2"][2], gamma=d["n2"][0], beta=d["n2"][1])
+        ops.gemm(xn, d["t_qkv_w"], qkv, bias=d["t_qkv_b"])
+        ops.small_attention(qkv, att, C * hwl, Fr, 8, hwl, R, hwl)
+        ops.gemm(att, d["t_o_w"], x, bias=d["t_o_b"], mode=ops.EPI_RESIDUAL, resid=x)
+        # multi-ID: the C tokens at one (frame, local position)
+        ops.layernorm_modulate(x, xn, eps=d["n3"][2], gamma=d["n3"][0], beta=d["n3"][1])
+        ops.gemm(xn, d["i_qkv_w"], qkv, bias=d["i_qkv_b"])
+        ops.small_attention(qkv, att, R, C, 8, R, 0, R)
+        ops.gemm(att, d["i_o_w"], x, bias=d["i_o_b"], mode=ops.EPI_RESIDUAL, resid=x)
+        # MLP (exact-erf GELU, ratio 1)
+        ops.layernorm_modulate(x, xn, eps=d["n4"][2], gamma=d["n4"][0], beta=d["n4"][1])
+        ops.gemm(xn, d["m0_w"], att, bias=d["m0_b"], act=ops.ACT_GELU_ERF)
+        ops.gemm(att, d["m2_w"], x, bias=d["m2_b"], mode=ops.EPI_RESIDUAL, resid=x)
+    r_loc = ws.get("rs_r_loc", (R, C), torch.float32)
+    ops.router_head(x, rp.head_w, rp.head_b, r_loc, R, C)
+    r_all = ws.get("rs_r_all", (P, Fr, hwl, C), torch.float32)
+    dist.all_gather_into_tensor(r_all, r_loc, group=group)
+    out.view(Fr, rs.hw, C).copy_(r_all.permute(1, 0, 2, 3).reshape(Fr, rs.hw_pad, C)[:, :rs.hw])
+    return out
+
+
 def router_forward_standalone(router, q_out, k_out, layer_idx):
     """Module-level entry (`MultiIPRouter.forward` signature): q_out [C,16,Nv,128] -> [1,Nv,C]."""
     C = k_out.shape[0]
@@ -166,6 +255,7 @@ class StepEngine:
         self._prologue_key = None
         self._prologue = None
         self._graphs: Dict[tuple, dict] = {}
+        self._router_shard = None
 
     # ------------------------------------------------------------------------------------------------ packing
     def _pack(self):
@@ -516,11 +606,17 @@ class StepEngine:
                     if use_router:
                         if P == 1:
                             q_all = qf
-                        else:  # the router needs whole frames: gather every rank's queries (router runs replicated)
+                        else:  # every rank needs the queries of its router positions in all frames: gather them
                             qg = ws.get("face_q_all", (N, dq))
                             dist.all_gather_into_tensor(qg, qpad, group=self.sp_group)
                             q_all = qg[T:]
-                        run_router(self.router, ws, q_all, pro["kmat"][b][ca], ca, C, Fr, hw, routing)
+                        if P > 1 and getattr(m, "sp_shard_router", True):
+                            rs = self._router_shard
+                            if rs is None or (rs.frames, rs.hw, rs.P) != (Fr, hw, P):
+                                rs = self._router_shard = RouterShard(self.router, Fr, hw, P, rank, dev)
+                            run_router_sp(self.router, rs, ws, q_all, pro["kmat"][b][ca], ca, C, routing, self.sp_group)
+                        else:
+                            run_router(self.router, ws, q_all, pro["kmat"][b][ca], ca, C, Fr, hw, routing)
                         if tap and b == 0:
                             tap(f"ca{ca}.router", routing)
                     if Vl:
