@@ -254,7 +254,9 @@ def main():
 
     model = build_model(cfg, dev)
     model.cache_prologue = False  # nothing is cached between timed steps
-    model.use_cuda_graph = world == 1 and not args.eager   # the step replays as one CUDA graph (prologue included)
+    # the step replays as one CUDA graph (prologue and, at N>1, the NCCL exchanges included); BYA_SP_GRAPH=0: eager at N>1
+    model.sp_cuda_graph = os.environ.get('BYA_SP_GRAPH', '1') == '1'
+    model.use_cuda_graph = not args.eager and (world == 1 or model.sp_cuda_graph)
     if world > 1:
         from bya_b200 import sp
 
@@ -380,6 +382,12 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        if model.use_cuda_graph:
+            # captured graphs hold NCCL work: tearing the process group down under them hung in round 1, so leave at once
+            sys.stdout.flush()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
         dist.destroy_process_group()
 
 

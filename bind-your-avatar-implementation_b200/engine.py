@@ -430,7 +430,8 @@ class StepEngine:
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             l0 = ops.LAUNCHES
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog thread of a sequence-parallel run may query events while we capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 out = self.step(**kw)
             g = dict(graph=graph, static=static, out=out, launches=ops.LAUNCHES - l0, pro=kw.get("_pro"), pro_key=key)
             self._graphs[sig] = g

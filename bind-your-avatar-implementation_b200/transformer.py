@@ -131,6 +131,7 @@ class BindyouravatarTransformer3DModel(nn.Module):
         self._processors: Dict[str, Any] = {}
         self.cache_prologue = True
         self.bounded_attention = True  # joint self-attention without a running max when the qk-LayerNorm bounds |q.k|
+        self.sp_cuda_graph = False   # also capture sequence-parallel steps (NCCL exchanges inside the graph)
         self.use_cuda_graph = False  # replay the step as one CUDA graph per input geometry (engine.step_graphed)
         self._sp_group = None  # set by bya_b200.sp.enable(): Ulysses sequence parallelism over this process group
 
@@ -288,7 +289,7 @@ class BindyouravatarTransformer3DModel(nn.Module):
         if denoise_step == 0:
             eng._prologue_key = None  # a new generation: recompute the timestep-invariant prologue
         # (sequence parallel stays eager: capturing the NCCL all-to-alls hung on the 2-GPU box in round 1)
-        if self.use_cuda_graph and taps is None and self._sp_group is None:
+        if self.use_cuda_graph and taps is None and (self._sp_group is None or self.sp_cuda_graph):
             out = eng.step_graphed(hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,
                                    audio_embeds if self.is_train_audio else None, af_matrix,
                                    routing_logits_forcing=routing_logits_forcing, per_frame_forcing=per_frame_forcing,
