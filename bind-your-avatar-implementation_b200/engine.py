@@ -139,7 +139,7 @@ class RouterShard:
     (all positions of one frame) needs an exchange: Ulysses over its 8 heads, q|k|v out / attention output back."""
 
     def __init__(self, rp: RouterPack, frames: int, hw: int, world: int, rank: int, device):
-        from .sp import qkv_rows_by_destination
+        from .sp import qkv_rows_by_destination, router_local_tokens
 
         if 8 % world:
             raise RuntimeError(f"bya_b200: the router's 8 heads are not divisible by the sequence-parallel size {world}")
@@ -147,9 +147,7 @@ class RouterShard:
         self.hwl = (hw + world - 1) // world
         self.hw_pad = self.hwl * world
         self.hl = 8 // world                      # spatial-attention heads per rank
-        j = torch.arange(self.hwl, device=device) + rank * self.hwl
-        f = torch.arange(frames, device=device)
-        self.idx = (f[:, None] * hw + j.clamp(max=hw - 1)[None, :]).reshape(-1)    # [F*hwl] global token of local row
+        self.idx = router_local_tokens(frames, hw, world, rank, device)    # [F*hwl] global token of each local row
         self.pos = rp.pos.index_select(0, self.idx).contiguous()
         self.blocks = [dict(w=qkv_rows_by_destination(d["s_qkv_w"], 512, world),
                             b=qkv_rows_by_destination(d["s_qkv_b"], 512, world)) for d in rp.blocks]
@@ -160,6 +158,8 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all: torch.
     """`run_router` sharded over the sequence-parallel group: q_all [Nv,2048] (every rank holds all face queries) ->
     out [Nv,C] fp32 on every rank.  Same kernels, same per-row arithmetic as the single-GPU router."""
     import torch.distributed as dist
+
+    from .sp import router_gather_positions, router_scatter_positions
 
     C, Fr, P, hwl, hl = chars, rs.frames, rs.P, rs.hwl, rs.hl
     R = Fr * hwl                 # local (frame, position) rows
@@ -192,10 +192,10 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all: torch.
         ops.layernorm_modulate(x, xn, eps=d["n1"][2], gamma=d["n1"][0], beta=d["n1"][1])
         ops.gemm(xn, dsp["w"], s_send[0], bias=dsp["b"], col_block=Ws, col_block_stride=M * Ws)
         dist.all_to_all_single(s_recv, s_send, group=group)
-        s_full.view(CF, P, hwl, Ws).copy_(s_recv.view(P, CF, hwl, Ws).permute(1, 0, 2, 3))
+        s_full.view(CF, P, hwl, Ws).copy_(router_gather_positions(s_recv, CF, P, hwl))
         ops.attention_d64(s_full[:, :Wo], s_full[:, Wo:2 * Wo], s_full[:, 2 * Wo:], s_att, CF, rs.hw, hl,
                           seq_stride=rs.hw_pad)
-        o_send.view(P, CF, hwl, Wo).copy_(s_att.view(CF, P, hwl, Wo).permute(1, 0, 2, 3))
+        o_send.view(P, CF, hwl, Wo).copy_(router_scatter_positions(s_att, CF, P, hwl))
         dist.all_to_all_single(o_recv, o_send, group=group)
         ops.gemm(o_recv[0], d["s_o_w"], x, bias=d["s_o_b"], mode=ops.EPI_RESIDUAL, resid=x, a_kblock=Wo,
                  a_kblock_stride=M * Wo)

@@ -40,6 +40,27 @@ def qkv_rows_by_destination(w_qkv: torch.Tensor, dim: int, world: int) -> torch.
     return torch.cat([w_qkv[t * dim + r * dl: t * dim + (r + 1) * dl] for r in range(world) for t in range(3)], 0).contiguous()
 
 
+# ---- sequence-parallel router layout (engine.RouterShard / run_router_sp): rank r owns the spatial positions
+# [r*hwl, (r+1)*hwl), hwl = ceil(hw / world), of every (character, frame); positions >= hw are padding
+def router_local_tokens(frames: int, hw: int, world: int, rank: int, device=None) -> torch.Tensor:
+    """Global video-token index (f*hw + position) of each local (frame, local position) row; padding rows repeat the
+    last real position of the frame."""
+    hwl = (hw + world - 1) // world
+    j = (torch.arange(hwl, device=device) + rank * hwl).clamp(max=hw - 1)
+    f = torch.arange(frames, device=device)
+    return (f[:, None] * hw + j[None, :]).reshape(-1)
+
+
+def router_gather_positions(recv: torch.Tensor, cf: int, world: int, hwl: int) -> torch.Tensor:
+    """All-to-all result [src][(c,f), src's positions][cols] -> view ordered [(c,f)][all positions (padded)][cols]."""
+    return recv.view(world, cf, hwl, -1).permute(1, 0, 2, 3)
+
+
+def router_scatter_positions(full: torch.Tensor, cf: int, world: int, hwl: int) -> torch.Tensor:
+    """[(c,f)][all positions (padded)][cols] -> view ordered [dest][(c,f), dest's positions][cols] (all-to-all input)."""
+    return full.view(cf, world, hwl, -1).permute(1, 0, 2, 3)
+
+
 def enable(model, group=None):
     """Turns on sequence parallelism for `model` over `group` (default: WORLD)."""
     import torch.distributed as dist

@@ -86,3 +86,48 @@ def test_ulysses_exchange_layouts_world2():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert len(ret) == world and all(v < 1e-4 for v in ret.values()), dict(ret)
+
+
+@pytest.mark.parametrize("world,hw", [(2, 54), (4, 54), (8, 1350), (2, 45)])
+def test_router_position_sharding_layouts(world, hw):
+    """The sequence-parallel router layout (engine.run_router_sp), simulated for all ranks in one process: every rank's
+    (character, frame, local position) rows cover the frame exactly once (padding = copies of the last position, at the
+    end), and send -> all-to-all -> gather / scatter -> all-to-all -> K-blocked operand round-trips the data."""
+    sys.path.insert(0, ROOT)
+    import bya_b200  # noqa: F401
+    from bya_b200.sp import qkv_rows_by_destination, router_gather_positions, router_local_tokens, router_scatter_positions
+
+    C, Fr, heads = 2, 3, 8
+    CF, hl = C * Fr, heads // world
+    hwl = (hw + world - 1) // world
+    Wo = hl * 64
+    idx = [router_local_tokens(Fr, hw, world, r) for r in range(world)]
+    cover = torch.cat([i.view(Fr, hwl) for i in idx], 1)[:, :hw]            # [F, hw] tokens in position order
+    assert torch.equal(cover, torch.arange(Fr * hw).view(Fr, hw))
+    for r in range(world):                                                   # padding repeats the last real position
+        pad = idx[r].view(Fr, hwl)[:, max(0, hw - r * hwl):]
+        assert bool((pad % hw == hw - 1).all())
+    # global activations X[c, f, j, head, 64]; rank r holds rows (c, f, its positions) of ALL heads
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(C, Fr, hwl * world, heads, 64, generator=g)
+    local = [X[:, :, r * hwl:(r + 1) * hwl].reshape(CF * hwl, heads * 64) for r in range(world)]
+    # "GEMM epilogue": destination-major column blocks [dest][rows][heads of dest]
+    send = [torch.stack([l[:, d * Wo:(d + 1) * Wo] for d in range(world)]) for l in local]     # [P][M, Wo] per rank
+    recv = [torch.stack([send[s][r] for s in range(world)]) for r in range(world)]             # all_to_all_single
+    for r in range(world):
+        full = router_gather_positions(recv[r], CF, world, hwl).reshape(CF, world * hwl, hl, 64)
+        assert torch.equal(full, X.reshape(CF, world * hwl, heads, 64)[:, :, r * hl:(r + 1) * hl])
+    # way back: each rank's [(c,f)][all positions][its heads] -> [dest][(c,f), dest's positions]
+    att = [X.reshape(CF, world * hwl, heads, 64)[:, :, r * hl:(r + 1) * hl].reshape(CF * world * hwl, Wo) for r in range(world)]
+    osend = [router_scatter_positions(a, CF, world, hwl).reshape(world, CF * hwl, Wo) for a in att]
+    orecv = [torch.stack([osend[s][r] for s in range(world)]) for r in range(world)]           # [src heads][local rows]
+    for r in range(world):
+        kblocked = torch.cat([orecv[r][s] for s in range(world)], 1)                           # K index = src*Wo + col
+        assert torch.equal(kblocked, local[r])
+    # weight rows reordered per destination reproduce the destination-major q|k|v column blocks
+    w = torch.arange(3 * 512 * 4, dtype=torch.float32).view(3 * 512, 4)
+    wr = qkv_rows_by_destination(w, 512, world)
+    dl = 512 // world
+    for d in range(world):
+        for t in range(3):
+            assert torch.equal(wr[(d * 3 + t) * dl:(d * 3 + t + 1) * dl], w[t * 512 + d * dl: t * 512 + (d + 1) * dl])
