@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "../../include/bya.h"
 
+#include <cstdlib>
+
 namespace bya {
 
 BYA_DEVICE void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
@@ -61,7 +63,11 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
     wt1[c] = (w && ok1) ? w[n1 * C + c] : 1.f;
   }
 
-  for (int h = 0; h < heads; ++h) {
+  // blockIdx.z = head group: one block per SM (143 blocks at the c2 size) left the kernel latency-bound (224 us
+  // against a 33 us HBM roofline); 4 head groups give every SM 3-4 resident blocks to overlap staging and math
+  const int hpg = (heads + gridDim.z - 1) / gridDim.z;
+  const int h_end = min(heads, int(blockIdx.z + 1) * hpg);
+  for (int h = blockIdx.z * hpg; h < h_end; ++h) {
     __syncthreads();
     // ---- stage K_h and V^T_h of every character (this block's frame) in shared memory
 #pragma unroll
@@ -368,7 +374,9 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
     return BYA_ERR_SHAPE;
   if (ldq % 2 || ldo % 2) return BYA_ERR_ALIGN;
   const int tpf = int(total_tokens / kv_frames);
-  dim3 grid((tpf + XA_TOK - 1) / XA_TOK, kv_frames);
+  static int xa_hpg = 0;   // heads per block (tuning knob BYA_XA_HPG)
+  if (!xa_hpg) { const char* e = std::getenv("BYA_XA_HPG"); xa_hpg = e ? std::atoi(e) : 4; if (xa_hpg < 1) xa_hpg = 4; }
+  dim3 grid((tpf + XA_TOK - 1) / XA_TOK, kv_frames, (heads + xa_hpg - 1) / xa_hpg);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const float sl2 = scale * 1.4426950408889634f;
 #define BYA_XA(D_, C_)                                                                                            \
