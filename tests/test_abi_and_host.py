@@ -134,3 +134,26 @@ def test_router_permutation_fold_identity():
     nat = q_out[0].transpose(0, 1).reshape(Nv, 2048)
     mine = torch.nn.functional.layer_norm(nat, (2048,), gamma[perm], beta[perm]) @ W[:, perm].t()
     assert float((ref[0] - mine).abs().max()) < 1e-9
+
+
+def test_mask_directory_loader_matches_reference_file_discovery(tmp_path):
+    """Host half of `bya_b200.masks` (no GPU): file discovery, binarisation and the reference's error (utils.py:853-879)."""
+    import numpy as np
+    from PIL import Image
+
+    import bya_b200  # noqa: F401
+    from bya_b200.masks import load_tracking_masks
+
+    rng = np.random.RandomState(0)
+    ref = (rng.rand(2, 5, 12, 16) > 0.6)
+    for c in range(2):
+        d = tmp_path / str(c + 1)
+        d.mkdir()
+        for t in range(5):
+            Image.fromarray((ref[c, t] * rng.randint(1, 255)).astype(np.uint8)).save(str(d / f"annotated_frame_{t:05d}.png"))
+    (tmp_path / "1" / "notes.txt").write_text("ignored")
+    m = load_tracking_masks(str(tmp_path))
+    assert m.dtype == torch.uint8 and tuple(m.shape) == (2, 5, 12, 16)
+    assert np.array_equal(m.numpy().astype(bool), ref)
+    with pytest.raises(ValueError):
+        load_tracking_masks(str(tmp_path / "1"))

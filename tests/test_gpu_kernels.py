@@ -319,6 +319,30 @@ def test_masks_to_routing_bit_exact_vs_reference_golden(ops, kind):
     assert np.array_equal(ored.cpu().numpy(), _c_oracle(masks, 13, 30, 45, frame_or=True)[1])
 
 
+@pytest.mark.parametrize("kind", ["moving", "overlap"])
+def test_mask_png_directories_to_routing_logits(ops, kind, tmp_path):
+    """The file-level entry (`bya_b200.masks.process_masks_to_routing_logits`, reference util/utils.py:871-936): PNG
+    directories written the way the SAM-2 stage does -> logits equal to the reference's output on the same files."""
+    from PIL import Image
+
+    from bya_b200 import masks as bm
+    from bya_b200.synth import tracking_masks
+
+    m = tracking_masks(kind)
+    for c in range(2):
+        d = tmp_path / str(c + 1)
+        d.mkdir()
+        for t in range(m.shape[1]):
+            Image.fromarray(m[c, t] * (200 if c else 1)).save(str(d / f"annotated_frame_{t:05d}.png"))   # any value > 0 counts
+    lg = bm.process_masks_to_routing_logits(str(tmp_path))
+    g = torch.load(os.path.join(GOLD, f"masks_{kind}.pt"))
+    assert lg.shape == (1, 17550, 2) and lg.dtype == torch.float32
+    assert torch.equal(lg.cpu(), g["routing_logits"].float())
+    (tmp_path / "2").rename(tmp_path / "two")
+    with pytest.raises(ValueError):
+        bm.process_masks_to_routing_logits(str(tmp_path))
+
+
 @pytest.mark.parametrize("geom", [(3, 97, 200, 300, 25, 10, 15), (2, 49, 480, 720, 13, 30, 45), (1, 13, 30, 45, 13, 30, 45),
                                   (3, 10, 33, 47, 13, 8, 12), (2, 1, 4, 4, 1, 1, 1)])
 def test_masks_to_routing_bit_exact_random_geometries(ops, geom):
