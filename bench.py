@@ -216,6 +216,8 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--layers", type=int, default=0, help="debug: override the layer count (the result is then NOT the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg-parallel", action="store_true",
+                    help="N>1, --config c3: the two CFG branches on the two halves of the GPUs (each half sequence-parallel)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -260,7 +262,10 @@ def main():
     if world > 1:
         from bya_b200 import sp
 
-        sp.enable(model, dist.group.WORLD)
+        if args.cfg_parallel:
+            sp.enable(model, cfg_parallel=True)
+        else:
+            sp.enable(model, dist.group.WORLD)
     inp = make_inputs(cfg, 1234, device=dev, dtype=torch.bfloat16)
 
     def one_step():
@@ -351,8 +356,9 @@ def main():
     if rank == 0:
         peaks, src = measured_peaks()
         N = cfg.n_tokens
-        heads_local = cfg.num_attention_heads // world
-        fa_flops = 4.0 * N * N * 64 * heads_local * cfg.batch  # algorithmic FLOPs of one self-attention launch
+        sp_world = world // 2 if args.cfg_parallel else world
+        heads_local = cfg.num_attention_heads // sp_world
+        fa_flops = 4.0 * N * N * 64 * heads_local   # algorithmic FLOPs of one self-attention launch (one batch element)
         achieved = fa_flops / (fa_ms * 1e-3) / 1e12 if fa_ms > 0 else None
         peak = peaks["bf16_tflops_sustained"]
         line = {
@@ -362,7 +368,8 @@ def main():
             "config": {"workload": f"{args.config}: {cfg.num_layers}-layer denoiser, 49f 480x720 (latent {cfg.frames}x60x90 -> "
                                    f"{cfg.n_tokens} tokens), {cfg.chars} characters, B={cfg.batch}, soft router, face+audio "
                                    "cross-attention, prologue recomputed every step",
-                       "parallelism": "single GPU" if world == 1 else f"ulysses sp{world}",
+                       "parallelism": "single GPU" if world == 1 else (f"cfg2 x ulysses sp{world // 2}" if args.cfg_parallel
+                                                                       else f"ulysses sp{world}"),
                        "launch": "one CUDA graph per step" if model.use_cuda_graph else "eager (one ctypes call per kernel)",
                        "l2": "working set (17 GB of weights + >1 GB activations per step) exceeds the 126 MB L2; no flush needed",
                        "weights": "random-init, seeded (bya_b200.synth)"},

@@ -61,13 +61,48 @@ def router_scatter_positions(full: torch.Tensor, cf: int, world: int, hwl: int) 
     return full.view(cf, world, hwl, -1).permute(1, 0, 2, 3)
 
 
-def enable(model, group=None):
-    """Turns on sequence parallelism for `model` over `group` (default: WORLD)."""
+def enable(model, group=None, cfg_parallel: bool = False):
+    """Turns on multi-GPU execution of `model`.
+
+    cfg_parallel=False: Ulysses sequence parallelism over `group` (default: WORLD).
+    cfg_parallel=True : the two classifier-free-guidance branches (batch elements 0 / 1 of every forward input; they are
+        independent inside the reference's forward — transformer.py:779, :870 loop over them) run batch-parallel: the
+        first half of WORLD takes element 0, the second half element 1, each half sequence-parallel inside; the two
+        predictions are exchanged once per step (pipeline_bindyouravatar.py:932-933 needs both).  SURVEY.md §8e."""
     import torch.distributed as dist
 
-    model._sp_group = group if group is not None else dist.group.WORLD
+    if not cfg_parallel:
+        model._sp_group = group if group is not None else dist.group.WORLD
+        model._cfg = None
+        model.invalidate()
+        return model
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if group is not None or world % 2:
+        raise RuntimeError("bya_b200: cfg_parallel splits WORLD in two halves (even world size, no sub-group)")
+    half = world // 2
+    halves = [dist.new_group(list(range(h * half, (h + 1) * half))) for h in range(2)]   # every rank creates both
+    model._cfg = dict(branch=rank // half, half=half, world=world)
+    model._sp_group = halves[rank // half] if half > 1 else None
     model.invalidate()
     return model
+
+
+def cfg_slice(x, branch: int):
+    """Batch element `branch` of a forward input (tensor, or nested list / tuple of tensors), keeping the batch axis."""
+    if isinstance(x, (list, tuple)):
+        return type(x)(cfg_slice(y, branch) for y in x)
+    if torch.is_tensor(x) and x.ndim > 0 and x.shape[0] == 2:
+        return x[branch:branch + 1]
+    return x
+
+
+def cfg_gather(out: torch.Tensor, cfg: dict) -> torch.Tensor:
+    """[1, ...] prediction of this rank's branch -> [2, ...] on every rank (one all-gather over WORLD; 2.2 MB per rank)."""
+    import torch.distributed as dist
+
+    allo = torch.empty((cfg["world"],) + tuple(out.shape[1:]), device=out.device, dtype=out.dtype)
+    dist.all_gather_into_tensor(allo, out.contiguous())
+    return torch.stack([allo[0], allo[cfg["half"]]])
 
 
 # ---- pure-torch statements of the two exchanges (any backend; used by the gloo tests as the layout specification)

@@ -134,6 +134,7 @@ class BindyouravatarTransformer3DModel(nn.Module):
         self.sp_cuda_graph = False   # also capture sequence-parallel steps (NCCL exchanges inside the graph)
         self.use_cuda_graph = False  # replay the step as one CUDA graph per input geometry (engine.step_graphed)
         self._sp_group = None  # set by bya_b200.sp.enable(): Ulysses sequence parallelism over this process group
+        self._cfg = None       # set by bya_b200.sp.enable(cfg_parallel=True): which CFG branch this rank computes
 
     # ------------------------------------------------------------------ reference surface: config / device / dtype
     @property
@@ -285,6 +286,16 @@ class BindyouravatarTransformer3DModel(nn.Module):
             raise NotImplementedError("bya_b200: timestep_cond is not used by the reference pipeline")
         if not torch.is_tensor(timestep):
             timestep = torch.tensor([timestep] * hidden_states.shape[0], dtype=torch.int64)
+        cfg = self._cfg
+        if cfg is not None:   # batch-parallel classifier-free guidance: this rank computes one of the two branches
+            from .sp import cfg_gather, cfg_slice
+
+            if hidden_states.shape[0] != 2:
+                raise RuntimeError("bya_b200: cfg_parallel expects the two CFG branches as a batch of 2")
+            br = cfg["branch"]
+            hidden_states, encoder_hidden_states, timestep = (cfg_slice(t, br) for t in (hidden_states, encoder_hidden_states, timestep))
+            id_cond, id_vit_hidden = cfg_slice(id_cond, br), cfg_slice(id_vit_hidden, br)
+            audio_embeds, af_matrix = cfg_slice(audio_embeds, br), cfg_slice(af_matrix, br)
         eng = self.engine()
         if denoise_step == 0:
             eng._prologue_key = None  # a new generation: recompute the timestep-invariant prologue
@@ -294,11 +305,15 @@ class BindyouravatarTransformer3DModel(nn.Module):
                                    audio_embeds if self.is_train_audio else None, af_matrix,
                                    routing_logits_forcing=routing_logits_forcing, per_frame_forcing=per_frame_forcing,
                                    cache_prologue=self.cache_prologue)
+            if cfg is not None:
+                out = cfg_gather(out, cfg)
             return (out, None, None, None, None)
         out = eng.step(hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,
                        audio_embeds if self.is_train_audio else None, af_matrix,
                        routing_logits_forcing=routing_logits_forcing, per_frame_forcing=per_frame_forcing,
                        cache_prologue=self.cache_prologue, taps=taps)
+        if cfg is not None:
+            out = cfg_gather(out, cfg)
         return (out, None, None, None, None)
 
     # ------------------------------------------------------------------ reference surface: checkpoint loading

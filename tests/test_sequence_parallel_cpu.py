@@ -131,3 +131,17 @@ def test_router_position_sharding_layouts(world, hw):
     for d in range(world):
         for t in range(3):
             assert torch.equal(wr[(d * 3 + t) * dl:(d * 3 + t + 1) * dl], w[t * 512 + d * dl: t * 512 + (d + 1) * dl])
+
+
+def test_cfg_slice_keeps_batch_axis_and_shared_inputs():
+    sys.path.insert(0, ROOT)
+    import bya_b200  # noqa: F401
+    from bya_b200.sp import cfg_slice
+
+    x = torch.arange(2 * 3 * 4).view(2, 3, 4)
+    assert torch.equal(cfg_slice(x, 1), x[1:2])
+    nested = [[torch.zeros(2, 5), torch.ones(2, 5)], (torch.full((2, 1), 7.0),)]
+    out = cfg_slice(nested, 0)
+    assert isinstance(out, list) and isinstance(out[1], tuple) and out[0][1].shape == (1, 5)
+    shared = torch.zeros(1, 10, 2)                      # forced routing logits are shared by both branches
+    assert cfg_slice(shared, 1) is shared and cfg_slice(None, 0) is None
