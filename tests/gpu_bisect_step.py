@@ -1,6 +1,6 @@
 """End-to-end parity of the CUDA step against the restated oracle on the GPU box (bisecting tool; prints per-tap error)."""
 import sys, os, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT)
 import torch
 import bya_b200
