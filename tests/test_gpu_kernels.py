@@ -196,6 +196,19 @@ def test_layernorm_modulate(ops, dim):
     out2 = torch.empty_like(x)
     ops.layernorm_modulate(x, out2)  # plain, no affine
     assert rel(out2, F.layer_norm(x.float(), (dim,))) < TOL
+    if dim >= 2048:   # many rows, ragged row count (not a multiple of the 8 rows per block), strided views
+        rows2 = 1031
+        big = rnd(rows2, dim + 64, s=2.0) + 0.25
+        xv = big[:, :dim]
+        outb = torch.zeros(rows2, dim + 64, device=dev, dtype=torch.bfloat16)
+        ops.layernorm_modulate(xv, outb[:, :dim], eps=1e-6, gamma=g, beta=b, mod_a=(sa, ha), mod_b=(sb, hb), split_row=226)
+        y = F.layer_norm(xv.float(), (dim,), g.float(), b.float(), 1e-6)
+        cls = (torch.arange(rows2, device=dev) < 226)[:, None]
+        y = y * (1 + torch.where(cls, sa[None], sb[None])) + torch.where(cls, ha[None], hb[None])
+        assert rel(outb[:, :dim], y) < TOL
+        assert bool((outb[:, dim:] == 0).all())
+        ops.layernorm_modulate(xv, outb[:, :dim], mod_b=(sb, hb))          # only the video class is modulated
+        assert rel(outb[:, :dim], F.layer_norm(xv.float(), (dim,)) * (1 + sb[None]) + hb[None]) < TOL
 
 
 def test_gemv_and_timestep_features(ops):
