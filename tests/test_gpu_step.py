@@ -212,3 +212,33 @@ def test_cuda_graph_replay_equals_eager(c1):
         m.engine()._graphs.clear()
     assert torch.equal(g0, eager[0]) and torch.equal(g3, eager[0])
     assert torch.equal(g1, eager[1]) and torch.equal(g2, eager[1])
+
+
+def test_weights_changed_in_place_are_repacked(c1):
+    """`pipe.fuse_lora` (infer.py:279; util/utils.py:1038-1041 targets attn1.to_q / to_k) rewrites weights in place after
+    the model was built: the packed copies (fused QKV, score bound, ...) must follow on the next forward, also in
+    CUDA-graph mode — SURVEY.md §8b."""
+    from bya_b200.synth import make_inputs
+    from oracle import restated
+
+    cfg, m, _ = c1
+    inp = make_inputs(cfg, 1234, device="cuda", dtype=torch.bfloat16)
+    w = m.transformer_blocks[0].attn1.to_q.weight
+    saved = w.detach().clone()
+    m.use_cuda_graph = True
+    try:
+        before = m(**inp)[0].clone()
+        with torch.no_grad():   # a rank-4 "LoRA" delta fused into to_q
+            g = torch.Generator(device="cuda").manual_seed(5)
+            a = torch.randn(w.shape[0], 4, device="cuda", generator=g) * 0.05
+            b = torch.randn(4, w.shape[1], device="cuda", generator=g) * 0.05
+            w.add_((a @ b).to(w.dtype))
+        after = m(**inp)[0].clone()
+        assert not torch.equal(before, after)
+        sd = {k: v.float() for k, v in m.state_dict().items()}
+        assert cos(after, restated.step(sd, cfg, **oracle_inputs(inp))) >= 0.999
+    finally:
+        with torch.no_grad():
+            w.copy_(saved)
+        m.use_cuda_graph = False
+        m.invalidate()
