@@ -157,3 +157,47 @@ def test_mask_directory_loader_matches_reference_file_discovery(tmp_path):
     assert np.array_equal(m.numpy().astype(bool), ref)
     with pytest.raises(ValueError):
         load_tracking_masks(str(tmp_path / "1"))
+
+
+def test_checkpoint_round_trip_through_the_reference_loaders(tmp_path):
+    """On-disk formats either side of the path: `from_pretrained_cus` (config.json + sharded
+    safetensors, a 32-channel patch_embed widened to 48 with zeros — transformer.py:1024-1093) and the three side files
+    `face_modules.pt` / `router_modules.pt` (transformer.py:461-513), on a tiny configuration.  (`audio_modules.pt` goes
+    through the same code path but always carries the 1.2 B-parameter Conv1d of AudioProjModel: left out to keep the CPU
+    suite small.)"""
+    from safetensors.torch import save_file
+
+    import bya_b200  # noqa: F401
+    from bya_b200.synth import fill_module
+    from bya_b200.transformer import BindyouravatarTransformer3DModel as M
+
+    kw = dict(num_attention_heads=2, attention_head_dim=64, in_channels=48, out_channels=16, num_layers=2,
+              text_embed_dim=64, time_embed_dim=32, cross_attn_interval=1, is_train_face=True, is_train_audio=False,
+              use_rotary_positional_embeddings=True)
+    src = M(**kw).eval()
+    fill_module(src, 3)
+    sd = src.state_dict()
+    base = {k: v.clone() for k, v in sd.items() if not k.startswith(("local_facial_extractor", "perceiver_cross_attention",
+                                                                     "router", "audio_model"))}
+    base["patch_embed.proj.weight"] = base["patch_embed.proj.weight"][:, :32].contiguous()   # CogVideoX-I2V has 32 channels
+    d = tmp_path / "ckpt" / "transformer"
+    d.mkdir(parents=True)
+    keys = sorted(base)
+    save_file({k: base[k].contiguous() for k in keys[: len(keys) // 2]}, str(d / "diffusion_pytorch_model-00001-of-00002.safetensors"))
+    save_file({k: base[k].contiguous() for k in keys[len(keys) // 2:]}, str(d / "diffusion_pytorch_model-00002-of-00002.safetensors"))
+    cfg = {k: v for k, v in kw.items() if k not in ("is_train_face", "is_train_audio", "cross_attn_interval")}
+    (d / "config.json").write_text(json.dumps(cfg))
+    src.save_face_modules(str(tmp_path / "face_modules.pt"))
+    src.save_router_modules(str(tmp_path / "router_modules.pt"))
+
+    dst = M.from_pretrained_cus(str(tmp_path / "ckpt"), subfolder="transformer",
+                                transformer_additional_kwargs=dict(is_train_face=True, is_train_audio=False, cross_attn_interval=1))
+    dst.load_face_modules(str(tmp_path / "face_modules.pt"), strict=False)
+    dst.load_router_modules(str(tmp_path / "router_modules.pt"), strict=False)
+    out = dst.state_dict()
+    assert set(out) == set(sd)
+    for k, v in sd.items():
+        if k == "patch_embed.proj.weight":
+            assert torch.equal(out[k][:, :32], v[:, :32]) and float(out[k][:, 32:].abs().max()) == 0.0
+        else:
+            assert torch.equal(out[k], v), k
