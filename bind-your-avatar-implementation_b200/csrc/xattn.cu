@@ -39,8 +39,10 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
   extern __shared__ __align__(16) uint8_t xa_smem[];
   typedef __nv_bfloat16 (*KTile)[32][KP];
   typedef __nv_bfloat16 (*VTile)[D][VP];
-  KTile sK = reinterpret_cast<KTile>(xa_smem);
-  VTile sV = reinterpret_cast<VTile>(xa_smem + size_t(C) * 32 * KP * 2);
+  // two staging buffers: K / V^T of head h+1 stream in (cp.async) while head h is being computed
+  constexpr size_t kBufBytes = size_t(C) * 32 * KP * 2 + size_t(C) * D * VP * 2;
+  auto kbuf = [&](int i) { return reinterpret_cast<KTile>(xa_smem + i * kBufBytes); };
+  auto vbuf = [&](int i) { return reinterpret_cast<VTile>(xa_smem + i * kBufBytes + size_t(C) * 32 * KP * 2); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -66,25 +68,39 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
   // blockIdx.z = head group: one block per SM (143 blocks at the c2 size) left the kernel latency-bound (224 us
   // against a 33 us HBM roofline); 4 head groups give every SM 3-4 resident blocks to overlap staging and math
   const int hpg = (heads + gridDim.z - 1) / gridDim.z;
-  const int h_end = min(heads, int(blockIdx.z + 1) * hpg);
-  for (int h = blockIdx.z * hpg; h < h_end; ++h) {
-    __syncthreads();
-    // ---- stage K_h and V^T_h of every character (this block's frame) in shared memory
+  const int h_begin = blockIdx.z * hpg, h_end = min(heads, int(blockIdx.z + 1) * hpg);
+  // ---- stage K_h and V^T_h of every character (this block's frame) into buffer `b` with 16-byte cp.async
+  auto stage = [&](int h, int b) {
+    KTile dK = kbuf(b);
+    VTile dV = vbuf(b);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const size_t grp = (size_t(c) * kv_frames + frame) * heads + h;
-      const uint4* gk = reinterpret_cast<const uint4*>(K + grp * 32 * D);
+      const __nv_bfloat16* gk = K + grp * 32 * D;
       for (int i = threadIdx.x; i < 32 * D / 8; i += blockDim.x) {
         const int row = i / (D / 8), cc = i % (D / 8);
-        *reinterpret_cast<uint4*>(&sK[c][row][cc * 8]) = gk[i];
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&dK[c][row][cc * 8])), "l"(gk + i * 8) : "memory");
       }
-      const uint4* gv = reinterpret_cast<const uint4*>(Vt + grp * 32 * D);
+      const __nv_bfloat16* gv = Vt + grp * 32 * D;
       for (int i = threadIdx.x; i < D * 32 / 8; i += blockDim.x) {
         const int row = i / 4, cc = i % 4;
-        *reinterpret_cast<uint4*>(&sV[c][row][cc * 8]) = gv[i];
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&dV[c][row][cc * 8])), "l"(gv + i * 8) : "memory");
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (h_begin < h_end) stage(h_begin, 0);
+  for (int h = h_begin; h < h_end; ++h) {
+    const int cur = (h - h_begin) & 1;
+    if (h + 1 < h_end) {
+      stage(h + 1, cur ^ 1);     // buffer cur^1 was last read in iteration h-1: every warp passed that iteration's trailing barrier
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
+    KTile sK = kbuf(cur);
+    VTile sV = vbuf(cur);
 
     // ---- Q fragments of this warp's 16 tokens for head h (straight from global; zero for rows past the frame)
     uint32_t qa[D / 16][4];
@@ -166,6 +182,7 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
       if (ok0) *reinterpret_cast<uint32_t*>(d0 + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0], o[nt][1]);
       if (ok1) *reinterpret_cast<uint32_t*>(d1 + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2], o[nt][3]);
     }
+    __syncthreads();   // everyone is done with buffer `cur` before the next iteration refills it
   }
 }
 
@@ -381,7 +398,7 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
   const float sl2 = scale * 1.4426950408889634f;
 #define BYA_XA(D_, C_)                                                                                            \
   do {                                                                                                            \
-    constexpr int smem = C_ * 32 * (D_ + 8) * 2 + C_ * D_ * 40 * 2;                                               \
+    constexpr int smem = 2 * (C_ * 32 * (D_ + 8) * 2 + C_ * D_ * 40 * 2);   /* two staging buffers */             \
     static bool attr = false;                                                                                     \
     if (!attr) {                                                                                                  \
       if (cudaFuncSetAttribute(xattn_kv32_kernel<D_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=   \
