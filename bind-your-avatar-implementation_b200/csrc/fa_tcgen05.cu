@@ -638,8 +638,13 @@ static int fa_launch(void* stream, const void* q, const void* k, const void* v, 
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
-  a.trace = nullptr;
-  if (const char* e = std::getenv("BYA_FA_TRACE")) a.trace = reinterpret_cast<long long*>(std::strtoull(e, nullptr, 0));
+  static long long* trace = nullptr;   // debug timeline buffer (tools/gpu_fa_trace.py), looked up once
+  static bool trace_looked_up = false;
+  if (!trace_looked_up) {
+    trace_looked_up = true;
+    if (const char* e = std::getenv("BYA_FA_TRACE")) trace = reinterpret_cast<long long*>(std::strtoull(e, nullptr, 0));
+  }
+  a.trace = trace;
   dim3 grid((seq + qt * FA_BM - 1) / (qt * FA_BM), heads, batch);
   kern[qt]<<<grid, threads[qt], fa_smem(qt), reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, a);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
