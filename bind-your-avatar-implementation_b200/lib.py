@@ -27,6 +27,19 @@ class ByaGemmArgs(ctypes.Structure):
     ]
 
 
+class ByaDpmStepArgs(ctypes.Structure):
+    _fields_ = [
+        ("frames", ctypes.c_int), ("channels", ctypes.c_int), ("hw", ctypes.c_int),
+        ("cfg_batch", ctypes.c_int), ("prediction_type", ctypes.c_int),
+        ("model_out", ctypes.c_void_p), ("model_out_f32", ctypes.c_void_p),
+        ("sample", ctypes.c_void_p), ("prev_sample", ctypes.c_void_p),
+        ("old_pred", ctypes.c_void_p), ("pred_out", ctypes.c_void_p),
+        ("noise", ctypes.c_void_p), ("model_input", ctypes.c_void_p),
+        ("in_batch", ctypes.c_int), ("in_channels", ctypes.c_int),
+        ("coef", ctypes.c_void_p), ("step_index", ctypes.c_void_p),
+    ]
+
+
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:

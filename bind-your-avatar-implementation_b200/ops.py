@@ -260,3 +260,71 @@ def audio_weights(af, routing, w, wsum=None):
     check(lib().bya_audio_weights(_stream(), _ptr(af), _ptr(routing), _ptr(w), _ptr(wsum), n, C), "audio_weights")
     _count()
     return w
+
+
+PRED_EPSILON, PRED_SAMPLE, PRED_V = 0, 1, 2
+DPM_NCOEF = 12   # include/bya.h BYA_DPM_*: guidance, sqrt_alpha, sqrt_beta, mult0..3, mult_noise, second_order, 1/sqrt_alpha
+
+
+def cfg_dpm_step(model_out, sample, prev_sample, old_pred, pred_out, noise, coef, *, prediction_type=PRED_V,
+                 step_index=None, model_input=None):
+    """Guidance combine + CogVideoXDPMScheduler.step + write of x_{t-1} into the next model input (one kernel).
+    model_out: bf16 [B, F, C, H, W] with B in {1, 2} (B = 2: [uncond | cond]) or fp32 [1, F, C, H, W] / [F, C, H, W];
+    sample / prev_sample: bf16 [.., F, C, H, W] (may alias); old_pred / pred_out: fp32 same numel (may alias);
+    noise: bf16 [steps, 2, numel]; coef: fp32 [steps, DPM_NCOEF]; step_index: int32 [1] on the device or None;
+    model_input: optional bf16 [Bin, F, Cin, H, W] whose channels [0, C) receive x_{t-1}."""
+    from .lib import ByaDpmStepArgs
+
+    F, C, H, W = sample.shape[-4:]
+    n = F * C * H * W
+
+    def chk(t, name, dtype, numel=None):
+        if t.dtype != dtype or not t.is_cuda or not t.is_contiguous() or (numel is not None and t.numel() != numel):
+            raise RuntimeError(f"bya_b200.cfg_dpm_step: {name} must be contiguous CUDA {dtype}"
+                               + (f" with {numel} elements" if numel is not None else ""))
+
+    chk(sample, "sample", torch.bfloat16, n), chk(prev_sample, "prev_sample", torch.bfloat16, n)
+    chk(old_pred, "old_pred", torch.float32, n), chk(pred_out, "pred_out", torch.float32, n)
+    chk(noise, "noise", torch.bfloat16), chk(coef, "coef", torch.float32)
+    if noise.dim() != 3 or noise.shape[1] != 2 or noise.shape[2] != n or coef.dim() != 2 or coef.shape[1] != DPM_NCOEF \
+            or coef.shape[0] != noise.shape[0]:
+        raise RuntimeError("bya_b200.cfg_dpm_step: noise must be [steps, 2, numel] and coef [steps, 12]")
+    a = ByaDpmStepArgs()
+    a.frames, a.channels, a.hw, a.prediction_type = F, C, H * W, prediction_type
+    if model_out.dtype == torch.float32:
+        chk(model_out, "model_out", torch.float32, n)
+        a.cfg_batch, a.model_out, a.model_out_f32 = 1, None, model_out.data_ptr()
+    else:
+        chk(model_out, "model_out", torch.bfloat16)
+        if model_out.numel() not in (n, 2 * n):
+            raise RuntimeError("bya_b200.cfg_dpm_step: model_out must hold one or two (CFG) predictions")
+        a.cfg_batch, a.model_out, a.model_out_f32 = model_out.numel() // n, model_out.data_ptr(), None
+    a.sample, a.prev_sample = sample.data_ptr(), prev_sample.data_ptr()
+    a.old_pred, a.pred_out, a.noise, a.coef = old_pred.data_ptr(), pred_out.data_ptr(), noise.data_ptr(), coef.data_ptr()
+    if step_index is not None:
+        if step_index.dtype != torch.int32 or not step_index.is_cuda:
+            raise RuntimeError("bya_b200.cfg_dpm_step: step_index must be a CUDA int32 tensor")
+        a.step_index = step_index.data_ptr()
+    elif coef.shape[0] != 1:
+        raise RuntimeError("bya_b200.cfg_dpm_step: without step_index pass exactly this step's coef row and noise pair")
+    if model_input is not None:
+        chk(model_input, "model_input", torch.bfloat16)
+        Bi, Fi, Ci, Hi, Wi = model_input.shape
+        if (Fi, Hi, Wi) != (F, H, W) or Ci < C:
+            raise RuntimeError("bya_b200.cfg_dpm_step: model_input must be [B, F, >=C, H, W]")
+        a.model_input, a.in_batch, a.in_channels = model_input.data_ptr(), Bi, Ci
+    check(lib().bya_cfg_dpm_step(_stream(), ctypes.byref(a)), "cfg_dpm_step")
+    _count()
+    return prev_sample, pred_out
+
+
+def denoise_select_step(timesteps, timestep_out, counter, step_index):
+    """timestep_out[:] = timesteps[*counter]; *step_index = *counter; *counter += 1 (all on the device)."""
+    if timesteps.dtype != torch.int64 or timestep_out.dtype != torch.int64 or counter.dtype != torch.int32 \
+            or step_index.dtype != torch.int32 or not (timesteps.is_cuda and timestep_out.is_cuda and counter.is_cuda
+                                                       and step_index.is_cuda):
+        raise RuntimeError("bya_b200.denoise_select_step: int64 timestep tensors and int32 counters on the device")
+    check(lib().bya_denoise_select_step(_stream(), _ptr(timesteps), timesteps.numel(), _ptr(timestep_out),
+                                        timestep_out.numel(), _ptr(counter), _ptr(step_index)), "denoise_select_step")
+    _count()
+    return timestep_out

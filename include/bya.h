@@ -152,6 +152,52 @@ int bya_routing_frame_or(void* stream, const float* logits, float* out, int fram
  * NULL): transformer.py:860-863,:899-900 */
 int bya_audio_weights(void* stream, const float* af, const float* routing, float* w, float* wsum, int tokens, int chars);
 
+/* ---------------------------------------------------------------- the step either side of the path
+ * Classifier-free-guidance combine + CogVideoXDPMScheduler.step + the write of x_{t-1} into the next step's model
+ * input, as ONE elementwise kernel (models/pipeline_bindyouravatar.py:897-906 concat / scale_model_input, :923-931
+ * guidance, :934-945 scheduler step and cast; the scheduler itself is diffusers 0.34.0.dev0
+ * schedulers/scheduling_dpm_cogvideox.py, not vendored in the reference).  Every product is rounded separately, in the
+ * dtype torch's promotion rules give the reference expression (0-dim coefficient x bf16 tensor -> bf16; x fp32
+ * tensor -> fp32), so the result is bit-identical to the reference arithmetic on the same noise draws.
+ *
+ * Per step the kernel reads one row of `coef` (device memory, so the launch can sit inside a CUDA graph that is
+ * replayed for every step): row = coef + BYA_DPM_NCOEF * (step_index ? *step_index : 0). */
+enum { BYA_DPM_GUIDANCE = 0,   /* guidance scale (only read when cfg_batch == 2) */
+       BYA_DPM_SQRT_ALPHA = 1, /* alphas_cumprod[t] ** 0.5 */
+       BYA_DPM_SQRT_BETA = 2,  /* (1 - alphas_cumprod[t]) ** 0.5 */
+       BYA_DPM_MULT0 = 3, BYA_DPM_MULT1 = 4, BYA_DPM_MULT2 = 5, BYA_DPM_MULT3 = 6, /* get_mult() */
+       BYA_DPM_MULT_NOISE = 7,
+       BYA_DPM_SECOND_ORDER = 8, /* != 0: old_pred_original_sample is not None and prev_timestep >= 0 */
+       BYA_DPM_INV_SQRT_ALPHA = 9, /* fp32(1 / alphas_cumprod[t] ** 0.5), the reciprocal taken in the table's precision:
+                                      what torch multiplies by for `tensor / cpu scalar` (epsilon prediction only) */
+       BYA_DPM_NCOEF = 12 };
+enum { BYA_PRED_EPSILON = 0, BYA_PRED_SAMPLE = 1, BYA_PRED_V = 2 };
+
+typedef struct ByaDpmStepArgs {
+  int frames, channels, hw;      /* latents are [frames, channels, hw] (one sample); channels * hw % 8 == 0 */
+  int cfg_batch;                 /* 1: model output is the prediction; 2: [uncond | cond], combined with the guidance */
+  int prediction_type;           /* BYA_PRED_* (CogVideoX: v_prediction) */
+  const bya_bf16* model_out;     /* bf16 [cfg_batch, frames, channels, hw] (the transformer's output), or NULL */
+  const float* model_out_f32;    /* fp32 [frames, channels, hw] when the caller already combined (cfg_batch == 1) */
+  const bya_bf16* sample;        /* x_t bf16 */
+  bya_bf16* prev_sample;         /* x_{t-1} bf16 (the reference casts to the prompt dtype, :945); may alias sample */
+  const float* old_pred;         /* previous step's pred_original_sample fp32; read only on second-order steps */
+  float* pred_out;               /* this step's pred_original_sample fp32; may alias old_pred */
+  const bya_bf16* noise;         /* bf16 [steps][2][frames*channels*hw]: the step's first / second randn draw */
+  bya_bf16* model_input;         /* optional bf16 [in_batch, frames, in_channels, hw]: channels [0, channels) of every
+                                    batch entry receive x_{t-1} (:897-906; scale_model_input is the identity) */
+  int in_batch, in_channels;
+  const float* coef;             /* device fp32 [steps][BYA_DPM_NCOEF] */
+  const int* step_index;         /* device, or NULL (row 0, noise pair 0) */
+} ByaDpmStepArgs;
+int bya_cfg_dpm_step(void* stream, const ByaDpmStepArgs* args);
+
+/* One thread: i = *counter; timestep_out[0..batch) = timesteps[i]; *step_index = i; *counter = i + 1.  Lets a captured
+ * graph [select, transformer step, bya_cfg_dpm_step] be replayed for the whole loop (:893-896, :908) with no host
+ * work between steps. */
+int bya_denoise_select_step(void* stream, const int64_t* timesteps, int n_steps, int64_t* timestep_out, int batch,
+                            int* counter, int* step_index);
+
 #ifdef __cplusplus
 }
 #endif
