@@ -64,9 +64,18 @@ class DenoiseLoop:
     def run(self, latents: torch.Tensor, image_latents: torch.Tensor, image_bg_latents: Optional[torch.Tensor],
             prompt_embeds: torch.Tensor, image_rotary_emb, id_cond, id_vit_hidden, audio_embeds, af_matrix,
             num_inference_steps: int = 50, generator=None, routing_logits_forcing=None, per_frame_forcing: bool = False,
-            noise: Optional[torch.Tensor] = None, trace: Optional[list] = None) -> torch.Tensor:
+            noise: Optional[torch.Tensor] = None, trace: Optional[list] = None,
+            conditions_cfg_batched: bool = True) -> torch.Tensor:
         """latents / image_latents / image_bg_latents: bf16 [1, F, 16, H, W]; the other conditions already carry the
-        CFG batch the way the pipeline prepares them (:877-884).  Returns the final latents bf16 [1, F, 16, H, W]."""
+        CFG batch the way the pipeline prepares them (:877-884), or pass conditions_cfg_batched=False to have
+        id_cond / id_vit_hidden / audio_embeds / af_matrix batched here (`conditions.prepare_cfg_conditions`;
+        prompt_embeds is always [negative | positive] as `encode_prompt` returns it).
+        Returns the final latents bf16 [1, F, 16, H, W]."""
+        if not conditions_cfg_batched:
+            from .conditions import prepare_cfg_conditions
+
+            id_cond, id_vit_hidden, audio_embeds, af_matrix = prepare_cfg_conditions(
+                id_cond, id_vit_hidden, audio_embeds, af_matrix, self.do_cfg, self.zero2cond)
         m, sch = self.transformer, self.scheduler
         if getattr(m, "_sp_group", None) is not None or getattr(m, "_cfg", None) is not None:
             raise NotImplementedError("bya_b200.DenoiseLoop: single-GPU loop; multi-GPU runs call the transformer per step")

@@ -199,3 +199,31 @@ def test_denoise_loop_graph_equals_eager_equals_pipeline_oracle(built, zero2cond
         assert torch.equal(trace[i][1], otrace[i][1]), f"pred_original_sample differs after step {i}"
     assert torch.equal(out_o, out_e)
     assert next(it, None) is None and torch.isfinite(out_e.float()).all()
+
+
+def test_denoise_loop_batches_the_conditions_like_the_pipeline(built):
+    """conditions_cfg_batched=False == passing what pipeline_bindyouravatar.py:877-884 would have built."""
+    import bya_b200  # noqa: F401
+    from bya_b200.conditions import prepare_cfg_conditions
+    from bya_b200.denoise import DenoiseLoop
+    from bya_b200.scheduler import CogVideoXDPMScheduler
+    from bya_b200.synth import CONFIGS, make_inputs
+    from test_gpu_step import build
+
+    cfg = CONFIGS["c1"]
+    m = build(cfg)
+    inp = make_inputs(cfg, 5, device="cuda", dtype=torch.bfloat16)
+    hs = inp["hidden_states"]
+    lat, img, bg = (hs[:1, :, 16 * k: 16 * (k + 1)].contiguous() for k in range(3))
+    prompt = torch.cat([torch.zeros_like(inp["encoder_hidden_states"]), inp["encoder_hidden_states"]])
+    outs = []
+    for batched in (True, False):
+        conds = (inp["id_cond"], inp["id_vit_hidden"], inp["audio_embeds"], inp["af_matrix"])
+        if batched:
+            conds = prepare_cfg_conditions(*conds, True, True)
+        loop = DenoiseLoop(m, CogVideoXDPMScheduler(), guidance_scale=4.0, zero2cond_cfg_flag=True)
+        outs.append(loop.run(lat, img, bg, prompt, inp["image_rotary_emb"], *conds, num_inference_steps=3,
+                             generator=torch.Generator(device="cuda").manual_seed(9),
+                             conditions_cfg_batched=batched).clone())
+    assert torch.equal(outs[0], outs[1]) and torch.isfinite(outs[0].float()).all()
+    assert not torch.equal(outs[0], lat)
