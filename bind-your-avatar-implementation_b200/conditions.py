@@ -4,7 +4,7 @@ audio-to-face assignment matrix (`models/utils.py:660-670`, `infer.py:148,164`).
 plain torch, no kernels."""
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Union
+from typing import Optional, Sequence, Union
 
 import torch
 

@@ -21,7 +21,7 @@ There is no fallback path: every op above is a libbya.so kernel.
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 

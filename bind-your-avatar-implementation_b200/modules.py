@@ -13,7 +13,6 @@ and the diffusers leaves named in SURVEY.md §8c.
 """
 from __future__ import annotations
 
-import math
 
 import torch
 import torch.nn.functional as F

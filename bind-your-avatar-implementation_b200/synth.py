@@ -8,8 +8,7 @@ number of layers, or on which object (reference module, oracle, this package) ow
 from __future__ import annotations
 
 import zlib
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from dataclasses import dataclass
 
 import torch
 
