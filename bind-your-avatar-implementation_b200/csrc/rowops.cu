@@ -1,6 +1,7 @@
 // HBM-bound row kernels of the denoising step: LayerNorm(+adaLN modulation), the adaLN/time-embedding GEMV,
 // sinusoidal timestep features, patchify / unpatchify, router output head.  One warp per row, 16-byte vector
 // loads, fp32 statistics — sized so every kernel is a single pass over its input.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/bya.h"
 
@@ -11,14 +12,15 @@ namespace bya {
 // Replaces nn.LayerNorm + the modulation arithmetic of diffusers CogVideoXLayerNormZero / AdaLayerNorm
 // (models/transformer.py:233, :251, :944-948), router / audio / face LayerNorms (router.py:247-248, :380-393,
 // :475-491; audio_model.py:249).
+#define BYA_LN_PARAMS                                                                                              \
+  const __nv_bfloat16 *__restrict__ x, int ldx, __nv_bfloat16 *__restrict__ out, int ldo, int rows, float eps,     \
+      const __nv_bfloat16 *__restrict__ gamma, const __nv_bfloat16 *__restrict__ beta,                             \
+      const float *__restrict__ scale_a, const float *__restrict__ shift_a, const float *__restrict__ scale_b,     \
+      const float *__restrict__ shift_b, int split_row, const __nv_bfloat16 *__restrict__ add, int add_rows
+#define BYA_LN_ARGS x, ldx, out, ldo, rows, eps, gamma, beta, scale_a, shift_a, scale_b, shift_b, split_row, add, add_rows
+
 template <int NV>  // NV = D / 256 : 16-byte vectors per lane
-__global__ void __launch_bounds__(256) ln_mod_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
-                                                     __nv_bfloat16* __restrict__ out, int ldo, int rows, float eps,
-                                                     const __nv_bfloat16* __restrict__ gamma,
-                                                     const __nv_bfloat16* __restrict__ beta,
-                                                     const float* __restrict__ scale_a, const float* __restrict__ shift_a,
-                                                     const float* __restrict__ scale_b, const float* __restrict__ shift_b,
-                                                     int split_row, const __nv_bfloat16* __restrict__ add, int add_rows) {
+BYA_DEVICE void ln_mod_row(BYA_LN_PARAMS) {
   constexpr int D = NV * 256;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,6 +99,21 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const __nv_bfloat16* __rest
     o.w = pack_bf16x2(y[6], y[7]);
     dst[i * 32 + lane] = o;
   }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_mod_kernel(BYA_LN_PARAMS) {
+  ln_mod_row<NV>(BYA_LN_ARGS);
+}
+// Same row code compiled for two blocks per SM (128 registers): 16 rows in flight per SM instead of 8 at D = 3072.
+template <int NV>
+__global__ void __launch_bounds__(256, 2) ln_mod_kernel_occ2(BYA_LN_PARAMS) {
+  ln_mod_row<NV>(BYA_LN_ARGS);
+}
+// ... and as 4-warp blocks, three per SM (168 registers, no spill): 12 rows in flight per SM.
+template <int NV>
+__global__ void __launch_bounds__(128, 3) ln_mod_kernel_occ3(BYA_LN_PARAMS) {
+  ln_mod_row<NV>(BYA_LN_ARGS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -236,6 +253,24 @@ extern "C" int bya_layernorm_modulate(void* stream, const void* x, int ldx, void
                                              shift_a, scale_b, shift_b, split_row, (const __nv_bfloat16*)add,        \
                                              add_rows);                                                              \
     break;
+  // 3072-wide rows: 4-warp blocks, three per SM (168 registers) by default — 53.9 us against 74.1 us for the 8-warp
+  // block (175 registers, one block per SM) and 56.4 us for the 128-register build, bit-identical results
+  // (tools/gpu_time_ln.py).  BYA_LN_OCC = 1 | 2 selects the other builds.
+  static const int occ = [] { const char* e = std::getenv("BYA_LN_OCC"); return e ? std::atoi(e) : 3; }();
+  if (dim == 3072 && occ == 2) {
+    ln_mod_kernel_occ2<12><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, rows, eps,
+                                                  (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, scale_a,
+                                                  shift_a, scale_b, shift_b, split_row, (const __nv_bfloat16*)add,
+                                                  add_rows);
+    return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
+  }
+  if (dim == 3072 && occ == 3) {
+    ln_mod_kernel_occ3<12><<<(rows + 3) / 4, 128, 0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, rows,
+                                                          eps, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+                                                          scale_a, shift_a, scale_b, shift_b, split_row,
+                                                          (const __nv_bfloat16*)add, add_rows);
+    return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
+  }
   switch (dim) {
     BYA_LN_CASE(2)
     BYA_LN_CASE(3)
