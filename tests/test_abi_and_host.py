@@ -201,3 +201,31 @@ def test_checkpoint_round_trip_through_the_reference_loaders(tmp_path):
             assert torch.equal(out[k][:, :32], v[:, :32]) and float(out[k][:, 32:].abs().max()) == 0.0
         else:
             assert torch.equal(out[k], v), k
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+    """`include/bya.h` is plain C: compile a probe with gcc that prints sizeof / offsetof of every field of the two
+    argument structs and compare with the ctypes mirrors in `bya_b200/lib.py` (a drifted field would silently shift
+    every later argument)."""
+    import ctypes
+    import subprocess
+
+    import bya_b200  # noqa: F401
+    from bya_b200.lib import ByaDpmStepArgs, ByaGemmArgs
+
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "bya.h")}"',
+             'int main(void) {']
+    for name, st in (("ByaGemmArgs", ByaGemmArgs), ("ByaDpmStepArgs", ByaDpmStepArgs)):
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in st._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, st in (("ByaGemmArgs", ByaGemmArgs), ("ByaDpmStepArgs", ByaDpmStepArgs)):
+        assert int(got[name]) == ctypes.sizeof(st), name
+        for field, _ in st._fields_:
+            assert int(got[f"{name}.{field}"]) == getattr(st, field).offset, f"{name}.{field}"
