@@ -137,3 +137,44 @@ def test_dynamic_guidance_matches_pipeline_formula():
         assert float(tab[i, 0]) == float(torch.tensor(dynamic_guidance(6.0, 50, t), dtype=torch.float32))
     assert float(DenoiseLoop(None, s, guidance_scale=6.5).coefficient_table(50)[7, 0]) == 6.5
     assert tab[0, 8] == 0 and tab[-1, 8] == 0 and bool((tab[1:-1, 8] == 1).all())
+
+
+def test_up_front_noise_draws_follow_the_reference_order():
+    """`DenoiseLoop.draw_noise` takes every step's randn up front; with the same seed it must hand step i exactly the
+    draws the step-by-step loop (oracle: pipeline :934-943 + scheduler.step) would have taken at step i — one on the
+    first / last step, two on second-order steps (the second one is the one that is used)."""
+    import bya_b200  # noqa: F401
+    from bya_b200.denoise import DenoiseLoop
+    from bya_b200.scheduler import CogVideoXDPMScheduler, randn_tensor
+    from oracle.dpm_oracle import DPMSchedulerOracle, denoise_loop_oracle
+
+    shape, steps = (1, 2, 16, 4, 6), 7
+    sch = CogVideoXDPMScheduler()
+    sch.set_timesteps(steps)
+    loop = DenoiseLoop(None, sch, guidance_scale=3.0)
+    noise = loop.draw_noise(shape, loop.coefficient_table(steps), torch.Generator().manual_seed(21), "cpu")
+    assert noise.shape == (steps, 2, 2 * 16 * 4 * 6) and noise.dtype == torch.bfloat16
+
+    g2, per_step, current = torch.Generator().manual_seed(21), [], []
+
+    def randn(s, dtype):
+        current.append(randn_tensor(s, g2, "cpu", dtype))
+        return current[-1]
+
+    def model(x, t, i):
+        if current:
+            per_step.append(list(current))
+            current.clear()
+        return torch.zeros(2, 2, 16, 4, 6, dtype=torch.bfloat16)
+
+    lat = torch.zeros(shape, dtype=torch.bfloat16)
+    denoise_loop_oracle(model, DPMSchedulerOracle(), lat, lat, lat, steps, 3.0, randn)
+    per_step.append(list(current))
+    # 7 trailing steps end on t = 142 with prev_timestep = 0: still a second-order step (unlike 50 steps, which end at -1)
+    assert [len(d) for d in per_step] == [1] + [2] * (steps - 1)
+    assert [len(d) for d in per_step] == [1 + int(v) for v in loop.coefficient_table(steps)[:, 8]]
+    for i, draws in enumerate(per_step):
+        for slot, d in enumerate(draws):
+            assert torch.equal(noise[i, slot], d.reshape(-1)), (i, slot)
+        if len(draws) == 1:
+            assert float(noise[i, 1].abs().max()) == 0.0
