@@ -19,7 +19,10 @@ namespace bya {
       const float *__restrict__ shift_b, int split_row, const __nv_bfloat16 *__restrict__ add, int add_rows
 #define BYA_LN_ARGS x, ldx, out, ldo, rows, eps, gamma, beta, scale_a, shift_a, scale_b, shift_b, split_row, add, add_rows
 
-template <int NV>  // NV = D / 256 : 16-byte vectors per lane
+// FLAGS >= 0 fixes at compile time which optional operands exist (bit 0: gamma AND beta, bit 1: modulation, bit 2:
+// additive table) — predicated-off code for absent operands still costs issue slots, and this kernel is half
+// issue-bound at D = 3072; FLAGS < 0 tests the pointers at run time (uncommon combinations).
+template <int NV, int FLAGS>  // NV = D / 256 : 16-byte vectors per lane
 BYA_DEVICE void ln_mod_row(BYA_LN_PARAMS) {
   constexpr int D = NV * 256;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -49,7 +52,11 @@ BYA_DEVICE void ln_mod_row(BYA_LN_PARAMS) {
   const float rstd = rsqrtf(warp_sum(var) * (1.f / D) + eps);
   const float* sc = (warp < split_row) ? scale_a : scale_b;
   const float* sh = (warp < split_row) ? shift_a : shift_b;
-  const uint4* addp = add ? reinterpret_cast<const uint4*>(add + size_t(warp % add_rows) * D) : nullptr;
+  const bool has_gamma = FLAGS < 0 ? gamma != nullptr : (FLAGS & 1) != 0;
+  const bool has_beta = FLAGS < 0 ? beta != nullptr : (FLAGS & 1) != 0;
+  const bool has_mod = FLAGS < 0 ? sc != nullptr : (FLAGS & 2) != 0;
+  const bool has_add = FLAGS < 0 ? add != nullptr : (FLAGS & 4) != 0;
+  const uint4* addp = has_add ? reinterpret_cast<const uint4*>(add + size_t(warp % add_rows) * D) : nullptr;
   uint4* dst = reinterpret_cast<uint4*>(out + size_t(warp) * ldo);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -57,7 +64,7 @@ BYA_DEVICE void ln_mod_row(BYA_LN_PARAMS) {
     float y[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] = (v[i * 8 + j] - mean) * rstd;
-    if (gamma) {
+    if (has_gamma) {
       const uint4 g = *reinterpret_cast<const uint4*>(gamma + c0);
       const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -66,7 +73,7 @@ BYA_DEVICE void ln_mod_row(BYA_LN_PARAMS) {
         y[2 * j + 1] *= bf16_hi(gw[j]);
       }
     }
-    if (beta) {
+    if (has_beta) {
       const uint4 g = *reinterpret_cast<const uint4*>(beta + c0);
       const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -75,7 +82,7 @@ BYA_DEVICE void ln_mod_row(BYA_LN_PARAMS) {
         y[2 * j + 1] += bf16_hi(gw[j]);
       }
     }
-    if (sc) {
+    if (has_mod) {
       const float4 s0 = *reinterpret_cast<const float4*>(sc + c0), s1 = *reinterpret_cast<const float4*>(sc + c0 + 4);
       const float4 h0 = *reinterpret_cast<const float4*>(sh + c0), h1 = *reinterpret_cast<const float4*>(sh + c0 + 4);
       const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
@@ -83,7 +90,7 @@ BYA_DEVICE void ln_mod_row(BYA_LN_PARAMS) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = y[j] * (1.f + ss[j]) + hh[j];
     }
-    if (addp) {
+    if (has_add) {
       const uint4 a = addp[i * 32 + lane];
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -101,19 +108,16 @@ BYA_DEVICE void ln_mod_row(BYA_LN_PARAMS) {
   }
 }
 
+// D = 3072 keeps the row in 96 fp32 registers per lane: 4-warp blocks, three per SM (168 registers, 12 rows in flight per
+// SM): 53.9 us at 17 776 rows against 74.1 us as one 8-warp block per SM (175 registers) — tools/gpu_time_ln.py.
 template <int NV>
-__global__ void __launch_bounds__(256) ln_mod_kernel(BYA_LN_PARAMS) {
-  ln_mod_row<NV>(BYA_LN_ARGS);
-}
-// Same row code compiled for two blocks per SM (128 registers): 16 rows in flight per SM instead of 8 at D = 3072.
-template <int NV>
-__global__ void __launch_bounds__(256, 2) ln_mod_kernel_occ2(BYA_LN_PARAMS) {
-  ln_mod_row<NV>(BYA_LN_ARGS);
-}
-// ... and as 4-warp blocks, three per SM (168 registers, no spill): 12 rows in flight per SM.
-template <int NV>
-__global__ void __launch_bounds__(128, 3) ln_mod_kernel_occ3(BYA_LN_PARAMS) {
-  ln_mod_row<NV>(BYA_LN_ARGS);
+struct LnLaunch {
+  static constexpr int kThreads = NV >= 12 ? 128 : 256;
+  static constexpr int kMinBlocks = NV >= 12 ? 3 : 2;
+};
+template <int NV, int FLAGS>
+__global__ void __launch_bounds__(LnLaunch<NV>::kThreads, LnLaunch<NV>::kMinBlocks) ln_mod_kernel(BYA_LN_PARAMS) {
+  ln_mod_row<NV, FLAGS>(BYA_LN_ARGS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -245,32 +249,24 @@ extern "C" int bya_layernorm_modulate(void* stream, const void* x, int ldx, void
   if (!scale_a && scale_b) split_row = 0;
   if (scale_a && !scale_b) split_row = rows;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int blocks = (rows + 7) / 8;
-#define BYA_LN_CASE(NV)                                                                                              \
-  case NV * 256:                                                                                                     \
-    ln_mod_kernel<NV><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, rows, eps,      \
-                                             (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, scale_a,       \
-                                             shift_a, scale_b, shift_b, split_row, (const __nv_bfloat16*)add,        \
-                                             add_rows);                                                              \
+  int flags = ((gamma && beta) ? 1 : 0) | ((scale_a || scale_b) ? 2 : 0) | (add ? 4 : 0);
+  if ((gamma == nullptr) != (beta == nullptr)) flags = -1;
+#define BYA_LN_LAUNCH(NV, FLAGS)                                                                                      \
+  ln_mod_kernel<NV, FLAGS><<<(rows * 32 + LnLaunch<NV>::kThreads - 1) / LnLaunch<NV>::kThreads, LnLaunch<NV>::kThreads, \
+                             0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, rows, eps,               \
+                                     (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, scale_a, shift_a,       \
+                                     scale_b, shift_b, split_row, (const __nv_bfloat16*)add, add_rows)
+#define BYA_LN_CASE(NV)                                                                                               \
+  case NV * 256:                                                                                                      \
+    switch (flags) {                                                                                                  \
+      case 0: BYA_LN_LAUNCH(NV, 0); break;  /* plain */                                                               \
+      case 1: BYA_LN_LAUNCH(NV, 1); break;  /* gamma, beta */                                                         \
+      case 2: BYA_LN_LAUNCH(NV, 2); break;  /* modulation only */                                                     \
+      case 3: BYA_LN_LAUNCH(NV, 3); break;  /* gamma, beta, modulation (adaLN) */                                     \
+      case 5: BYA_LN_LAUNCH(NV, 5); break;  /* gamma, beta, additive table (router positions) */                      \
+      default: BYA_LN_LAUNCH(NV, -1); break;                                                                          \
+    }                                                                                                                 \
     break;
-  // 3072-wide rows: 4-warp blocks, three per SM (168 registers) by default — 53.9 us against 74.1 us for the 8-warp
-  // block (175 registers, one block per SM) and 56.4 us for the 128-register build, bit-identical results
-  // (tools/gpu_time_ln.py).  BYA_LN_OCC = 1 | 2 selects the other builds.
-  static const int occ = [] { const char* e = std::getenv("BYA_LN_OCC"); return e ? std::atoi(e) : 3; }();
-  if (dim == 3072 && occ == 2) {
-    ln_mod_kernel_occ2<12><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, rows, eps,
-                                                  (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, scale_a,
-                                                  shift_a, scale_b, shift_b, split_row, (const __nv_bfloat16*)add,
-                                                  add_rows);
-    return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
-  }
-  if (dim == 3072 && occ == 3) {
-    ln_mod_kernel_occ3<12><<<(rows + 3) / 4, 128, 0, s>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, rows,
-                                                          eps, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-                                                          scale_a, shift_a, scale_b, shift_b, split_row,
-                                                          (const __nv_bfloat16*)add, add_rows);
-    return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
-  }
   switch (dim) {
     BYA_LN_CASE(2)
     BYA_LN_CASE(3)
@@ -281,6 +277,7 @@ extern "C" int bya_layernorm_modulate(void* stream, const void* x, int ldx, void
       return BYA_ERR_SHAPE;
   }
 #undef BYA_LN_CASE
+#undef BYA_LN_LAUNCH
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }
 

@@ -196,6 +196,15 @@ def test_layernorm_modulate(ops, dim):
     out2 = torch.empty_like(x)
     ops.layernorm_modulate(x, out2)  # plain, no affine
     assert rel(out2, F.layer_norm(x.float(), (dim,))) < TOL
+    # the operand combinations that have their own compiled variant, and one that takes the run-time-flag path
+    ops.layernorm_modulate(x, out2, gamma=g, beta=b)
+    assert rel(out2, F.layer_norm(x.float(), (dim,), g.float(), b.float())) < TOL
+    ops.layernorm_modulate(x, out2, gamma=g, beta=b, add=add)
+    assert rel(out2, F.layer_norm(x.float(), (dim,), g.float(), b.float()) + add.float()[torch.arange(rows, device=dev) % 50]) < TOL
+    ops.layernorm_modulate(x, out2, mod_a=(sa, ha), mod_b=(sb, hb), split_row=split)
+    assert rel(out2, F.layer_norm(x.float(), (dim,)) * (1 + torch.where(cls, sa[None], sb[None])) + torch.where(cls, ha[None], hb[None])) < TOL
+    ops.layernorm_modulate(x, out2, gamma=g, add=add)   # gamma without beta
+    assert rel(out2, F.layer_norm(x.float(), (dim,)) * g.float() + add.float()[torch.arange(rows, device=dev) % 50]) < TOL
     if dim >= 2048:   # many rows, ragged row count (not a multiple of the 8 rows per block), strided views
         rows2 = 1031
         big = rnd(rows2, dim + 64, s=2.0) + 0.25
