@@ -362,7 +362,7 @@ def main():
 
         hs = inp["hidden_states"]
         lat, img, bg = (hs[:1, :, 16 * k: 16 * (k + 1)].contiguous() for k in range(3))
-        loop = DenoiseLoop(model, CogVideoXDPMScheduler(), guidance_scale=6.0, do_classifier_free_guidance=cfg.batch == 2)
+        loop = DenoiseLoop(model, CogVideoXDPMScheduler.cogvideox_5b(), guidance_scale=6.0, do_classifier_free_guidance=cfg.batch == 2)
         n_loop = max(args.steps, 4)
         l1 = ops.LAUNCHES
         loop.run(lat, img, bg, inp["encoder_hidden_states"], inp["image_rotary_emb"], inp["id_cond"], inp["id_vit_hidden"],

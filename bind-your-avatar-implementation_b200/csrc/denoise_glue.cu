@@ -115,6 +115,8 @@ extern "C" int bya_cfg_dpm_step(void* stream, const ByaDpmStepArgs* p) {
   if (!a.sample || !a.prev_sample || !a.pred_out || !a.noise || !a.coef || !a.old_pred) return BYA_ERR_SHAPE;
   if (a.model_input && (a.in_batch <= 0 || a.in_channels < a.channels)) return BYA_ERR_SHAPE;
   if (((long long)a.channels * a.hw) % 8 != 0) return BYA_ERR_SHAPE;
+  // the model-input write uses 16-byte stores at a frame stride of in_channels * hw elements
+  if (a.model_input && ((long long)a.in_channels * a.hw) % 8 != 0) return BYA_ERR_SHAPE;
   const uintptr_t bits = (uintptr_t)a.model_out | (uintptr_t)a.model_out_f32 | (uintptr_t)a.sample |
                          (uintptr_t)a.prev_sample | (uintptr_t)a.old_pred | (uintptr_t)a.pred_out |
                          (uintptr_t)a.noise | (uintptr_t)a.model_input;

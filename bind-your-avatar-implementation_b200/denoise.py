@@ -110,7 +110,7 @@ class DenoiseLoop:
         kw = dict(hidden_states=x, encoder_hidden_states=prompt_embeds.to(dev), timestep=st["t"],
                   image_rotary_emb=tuple(t.to(dev) for t in image_rotary_emb), id_cond=[t.to(dev) for t in id_cond],
                   id_vit_hidden=[[v.to(dev) for v in l] for l in id_vit_hidden],
-                  audio_embeds=None if aud is None else aud.to(dev), af_matrix=af_matrix.to(dev),
+                  audio_embeds=None if aud is None else aud.to(dev), af_matrix=None if af_matrix is None else af_matrix.to(dev),
                   routing_logits_forcing=None if use_router else routing_logits_forcing.to(dev),
                   per_frame_forcing=per_frame_forcing, cache_prologue=False)
         kw["_pro"] = eng.prologue(kw["id_cond"], kw["id_vit_hidden"], kw["audio_embeds"], F, use_router)

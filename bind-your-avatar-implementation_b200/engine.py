@@ -249,6 +249,8 @@ class StepEngine:
         self.heads = cfg.num_attention_heads
         if cfg.attention_head_dim != 64:
             raise RuntimeError("bya_b200: attention_head_dim must be 64")
+        if cfg.patch_size != 2:
+            raise RuntimeError("bya_b200: patchify / unpatchify kernels are built for patch_size == 2")
         self.L = cfg.num_layers
         self.ws = _Workspace(self.device)
         self._pack()
@@ -381,11 +383,20 @@ class StepEngine:
             L_["w_qkv_sp"] = qkv_rows_by_destination(L_["w_qkv"], self.D, P)
             L_["b_qkv_sp"] = qkv_rows_by_destination(L_["b_qkv"], self.D, P)
 
-    @staticmethod
-    def _prologue_cache_key(id_cond, id_vit_hidden, audio_embeds, frames, use_router):
-        """Identity of the timestep-invariant inputs (the pipeline passes the same tensors on all 50 steps)."""
+    def _prologue_cache_key(self, id_cond, id_vit_hidden, audio_embeds, frames, use_router):
+        """Identity of the timestep-invariant inputs (the pipeline passes the same tensors on all 50 steps).  The key
+        is (address, version, shape) per tensor; `_prologue_refs` keeps the keyed tensors of the cached generation
+        alive, so the caching allocator cannot hand their addresses (with a fresh version counter) to the next
+        generation's inputs while the cache still answers for them."""
         ts = list(id_cond) + [v for l in id_vit_hidden for v in l] + ([audio_embeds] if audio_embeds is not None else [])
+        self._prologue_refs_pending = ts
         return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts) + (frames, use_router)
+
+    def new_generation(self):
+        """`denoise_step == 0` (transformer.py forward kwarg): drop every cached prologue, eager and graphed."""
+        self._prologue_key = None
+        for g in self._graphs.values():
+            g["pro_key"] = None
 
     # ------------------------------------------------------------------------------------------------ CUDA-graph replay
     @torch.no_grad()
@@ -397,7 +408,7 @@ class StepEngine:
         stream); the returned tensor is the graph's static output (valid until the next call)."""
         dev = self.device
         nested = dict(hidden_states=hidden_states, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
-                      image_rotary_emb=list(image_rotary_emb), id_cond=list(id_cond),
+                      image_rotary_emb=None if image_rotary_emb is None else list(image_rotary_emb), id_cond=list(id_cond),
                       id_vit_hidden=[list(l) for l in id_vit_hidden], audio_embeds=audio_embeds, af_matrix=af_matrix,
                       routing_logits_forcing=routing_logits_forcing)
 
@@ -419,7 +430,8 @@ class StepEngine:
         g = self._graphs.get(sig)
         if g is None:
             static = {k: like(v) for k, v in nested.items()}
-            kw = dict(static, image_rotary_emb=tuple(static["image_rotary_emb"]), per_frame_forcing=per_frame_forcing,
+            rope = static["image_rotary_emb"]
+            kw = dict(static, image_rotary_emb=None if rope is None else tuple(rope), per_frame_forcing=per_frame_forcing,
                       cache_prologue=False)
             if cache_prologue:   # the prologue stays outside the graph: it is recomputed only when its inputs change
                 kw["_pro"] = self.prologue(static["id_cond"], static["id_vit_hidden"], static["audio_embeds"], Fr, use_router)
@@ -433,7 +445,8 @@ class StepEngine:
             # thread_local: the NCCL watchdog thread of a sequence-parallel run may query events while we capture
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 out = self.step(**kw)
-            g = dict(graph=graph, static=static, out=out, launches=ops.LAUNCHES - l0, pro=kw.get("_pro"), pro_key=key)
+            g = dict(graph=graph, static=static, out=out, launches=ops.LAUNCHES - l0, pro=kw.get("_pro"), pro_key=key,
+                     pro_refs=self._prologue_refs_pending if cache_prologue else None)
             self._graphs[sig] = g
         else:
             for dst, src in zip(flat(list(g["static"].values())), flat(list(nested.values()))):
@@ -445,7 +458,7 @@ class StepEngine:
                 for dst, src in zip(flat(_tree_values(g["pro"])), flat(_tree_values(new))):
                     if dst is not None:
                         dst.copy_(src)
-                g["pro_key"] = key
+                g["pro_key"], g["pro_refs"] = key, self._prologue_refs_pending
         g["graph"].replay()
         ops.LAUNCHES += g["launches"]
         return g["out"]
@@ -467,7 +480,9 @@ class StepEngine:
         C = len(id_cond)
         use_router = routing_logits_forcing is None
         has_audio = audio_embeds is not None and len(self.audio) > 0
-        tap = (lambda k, v: taps.__setitem__(k, v.detach().float().cpu().clone())) if taps is not None else None
+        # taps: a dict (filled with fp32 CPU copies) or a callable(name, device tensor) — single-GPU debugging aid
+        tap = taps if callable(taps) else (
+            (lambda k, v: taps.__setitem__(k, v.detach().float().cpu().clone())) if taps is not None else None)
         # ---- this rank's slice of the [text; video] token axis
         P, rank = getattr(self, "sp_size", 1), getattr(self, "sp_rank", 0)
         if P > 1:
@@ -485,8 +500,9 @@ class StepEngine:
         Dl, Hl_ = D // P, self.heads // P
         if m.is_train_face:
             m.router.set_grid(Fr, gh, gw)
-            if self.router.pos.shape[0] != Nv:
+            if getattr(self, "_router_grid", None) != (Fr, gh, gw):   # also catches 30x45 -> 45x30 (same row count)
                 self.router = RouterPack(m.router)
+                self._router_grid = (Fr, gh, gw)
 
         # ---- prologue (cached per generation)
         if _pro is not None:
@@ -496,6 +512,7 @@ class StepEngine:
             if key is None or key != self._prologue_key:
                 self._prologue = self.prologue(id_cond, id_vit_hidden, audio_embeds, Fr, use_router)
                 self._prologue_key = key
+                self._prologue_refs = self._prologue_refs_pending if cache_prologue else None
             pro = self._prologue
         if tap:
             tap("face_tokens", pro["face_tokens"])
@@ -518,7 +535,22 @@ class StepEngine:
         if tap:
             tap("temb", temb)
 
+        if image_rotary_emb is None:   # non-RoPE configuration: the QKV epilogue rotates by the identity
+            idt = getattr(self, "_rope_identity", None)
+            if idt is None or idt[0].shape[0] != Nv:
+                idt = self._rope_identity = (torch.ones(Nv, 64, device=dev), torch.zeros(Nv, 64, device=dev))
+            image_rotary_emb = idt
         cos, sin = (t.to(dev, torch.float32).contiguous() for t in image_rotary_emb)
+        # joint positional table of the sincos / learned (CogVideoX-5B-I2V) configurations (transformer.py:370-392)
+        pos_tab = m.patch_embed.table_for(Fr, Hl, Wl)
+        if pos_tab is not None:
+            if pos_tab.shape[1] != N:
+                raise RuntimeError(f"bya_b200: positional table has {pos_tab.shape[1]} rows, the input {N} tokens "
+                                   "(text length must equal max_text_seq_length)")
+            pk = (pos_tab.data_ptr(), pos_tab._version, tuple(pos_tab.shape))
+            if getattr(self, "_pos_key", None) != pk:
+                self._pos_bf, self._pos_key = _bf(pos_tab[0].to(dev)), pk
+            pos_tab = self._pos_bf
         forced = None
         if not use_router:
             forced = routing_logits_forcing.to(dev, torch.float32).reshape(Nv, C).contiguous()
@@ -554,8 +586,11 @@ class StepEngine:
             if Tl:
                 ops.gemm(txt[b][n0:n0 + Tl], self.text_w, x[:Tl], bias=self.text_b)
             ops.patchify(lat[b], patches)
-            if Vl:
+            if Vl and pos_tab is None:
                 ops.gemm(patches[v0:v0 + Vl], self.patch_w, xv, bias=self.patch_b)
+            elif Vl:   # text rows of the table are zero; the video rows ride in as the epilogue's residual operand
+                ops.gemm(patches[v0:v0 + Vl], self.patch_w, xv, bias=self.patch_b, mode=ops.EPI_RESIDUAL,
+                         resid=pos_tab[T + v0: T + v0 + Vl])
             if tap and b == 0:
                 tap("embed_video", xv)
             routing.zero_()

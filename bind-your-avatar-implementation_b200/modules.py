@@ -83,11 +83,73 @@ class TimestepEmbedding(nn.Module):
         self.linear_2 = nn.Linear(out_dim, out_dim)
 
 
+def sincos_table_1d(dim, pos):
+    """[len(pos), dim] = [sin(pos * w) | cos(pos * w)], w_k = 10000^(-k / (dim/2)) evaluated in float64 (the published
+    diffusers `get_1d_sincos_pos_embed_from_grid`)."""
+    w = 1.0 / 10000 ** (torch.arange(dim // 2, dtype=torch.float64) / (dim / 2.0))
+    a = torch.outer(pos.reshape(-1), w)
+    return torch.cat([a.sin(), a.cos()], dim=1)
+
+
+def sincos_positional_embedding(dim, frames, grid_h, grid_w, text_len, spatial_scale=1.875, temporal_scale=1.0):
+    """CogVideoX's joint positional table [1, text_len + frames*grid_h*grid_w, dim] (diffusers `CogVideoXPatchEmbed.
+    _get_positional_embeddings` / `get_3d_sincos_pos_embed`, restated from the published algorithm): text rows are
+    zero; a video row (f, h, w) is [temporal dim/4 | w-axis 3dim/8 | h-axis 3dim/8], each [sin | cos]."""
+    d_sp, d_t = 3 * dim // 4, dim // 4
+    ph = torch.arange(grid_h, dtype=torch.float32) / spatial_scale
+    pw = torch.arange(grid_w, dtype=torch.float32) / spatial_scale
+    ew = sincos_table_1d(d_sp // 2, pw)[None, :, :].expand(grid_h, -1, -1)
+    eh = sincos_table_1d(d_sp // 2, ph)[:, None, :].expand(-1, grid_w, -1)
+    sp = torch.cat([ew, eh], dim=-1).reshape(1, grid_h * grid_w, d_sp).expand(frames, -1, -1)
+    et = sincos_table_1d(d_t, torch.arange(frames, dtype=torch.float32) / temporal_scale)
+    et = et[:, None, :].expand(-1, grid_h * grid_w, -1)
+    video = torch.cat([et, sp], dim=-1).reshape(frames * grid_h * grid_w, dim).float()
+    out = torch.zeros(1, text_len + video.shape[0], dim)
+    out[0, text_len:] = video
+    return out
+
+
 class PatchEmbed(nn.Module):
-    def __init__(self, patch, in_ch, dim, text_dim):
+    """Parameter layout of diffusers `CogVideoXPatchEmbed`: proj (Conv2d k=s=patch), text_proj, and — for the
+    non-RoPE (`use_positional_embeddings`) and the CogVideoX-5B-I2V (`use_learned_positional_embeddings`)
+    configurations — the joint positional table `pos_embedding`, a checkpoint key only when learned
+    (models/transformer.py:370-392)."""
+
+    def __init__(self, patch, in_ch, dim, text_dim, sample_width=90, sample_height=60, sample_frames=49,
+                 temporal_compression_ratio=4, max_text_seq_length=226, spatial_interpolation_scale=1.875,
+                 temporal_interpolation_scale=1.0, use_positional_embeddings=False, use_learned_positional_embeddings=False):
         super().__init__()
+        self.patch_size, self.embed_dim = patch, dim
         self.proj = nn.Conv2d(in_ch, dim, kernel_size=(patch, patch), stride=patch)
         self.text_proj = nn.Linear(text_dim, dim)
+        self.sample_width, self.sample_height, self.sample_frames = sample_width, sample_height, sample_frames
+        self.temporal_compression_ratio, self.max_text_seq_length = temporal_compression_ratio, max_text_seq_length
+        self.spatial_interpolation_scale = spatial_interpolation_scale
+        self.temporal_interpolation_scale = temporal_interpolation_scale
+        self.use_positional_embeddings = use_positional_embeddings
+        self.use_learned_positional_embeddings = use_learned_positional_embeddings
+        if use_positional_embeddings or use_learned_positional_embeddings:
+            self.register_buffer("pos_embedding", self.positional_table(sample_height, sample_width, sample_frames),
+                                 persistent=use_learned_positional_embeddings)
+
+    def positional_table(self, height, width, pixel_frames):
+        frames = (pixel_frames - 1) // self.temporal_compression_ratio + 1
+        return sincos_positional_embedding(self.embed_dim, frames, height // self.patch_size, width // self.patch_size,
+                                           self.max_text_seq_length, self.spatial_interpolation_scale,
+                                           self.temporal_interpolation_scale)
+
+    def table_for(self, latent_frames, height, width):
+        """The table the reference adds for an input of this geometry, or None (RoPE-only configuration).  The learned
+        table cannot change resolution (diffusers raises the same ValueError)."""
+        if not (self.use_positional_embeddings or self.use_learned_positional_embeddings):
+            return None
+        if self.use_learned_positional_embeddings and (self.sample_width != width or self.sample_height != height):
+            raise ValueError("It is currently not possible to generate videos at a different resolution that the defaults. "
+                             "This should only be the case with 'THUDM/CogVideoX-5b-I2V'.")
+        pixel_frames = (latent_frames - 1) * self.temporal_compression_ratio + 1
+        if (self.sample_height, self.sample_width, self.sample_frames) != (height, width, pixel_frames):
+            return self.positional_table(height, width, pixel_frames).to(self.pos_embedding.device, self.pos_embedding.dtype)
+        return self.pos_embedding
 
 
 class CogVideoXBlock(nn.Module):

@@ -40,15 +40,30 @@ def randn_tensor(shape, generator=None, device=None, dtype=None):
     return torch.randn(tuple(shape), generator=generator, device=draw_on, dtype=dtype).to(device)
 
 
+# What the CogVideoX-5B (and 5B-I2V) `scheduler/scheduler_config.json` supplies — the values the reference pipeline
+# actually runs with (`infer.py:202` loads them with `from_pretrained(model_path, subfolder="scheduler")`).  The
+# constructor DEFAULTS below are the published class's own (epsilon / leading / no rescale / snr_shift_scale 3.0).
+COGVIDEOX_5B_SCHEDULER_CONFIG = dict(
+    num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+    set_alpha_to_one=True, steps_offset=0, prediction_type="v_prediction", clip_sample_range=1.0, sample_max_value=1.0,
+    timestep_spacing="trailing", rescale_betas_zero_snr=True, snr_shift_scale=1.0)
+
+
 class CogVideoXDPMScheduler:
+    """NOTE for integrators: `pipeline_bindyouravatar.py:936` picks the (model_output, old_pred_original_sample, timestep,
+    timestep_back, sample) call form with `isinstance(self.scheduler, CogVideoXDPMScheduler)` against the class IT
+    imported — import this class under that name in the pipeline module, otherwise the DDIM-style
+    call form is used and the arguments bind wrongly."""
+
     order = 1
     init_noise_sigma = 1.0
+    config_name = "scheduler_config.json"
 
     def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.0120,
-                 beta_schedule: str = "scaled_linear", trained_betas=None, clip_sample: bool = False,
-                 set_alpha_to_one: bool = True, steps_offset: int = 0, prediction_type: str = "v_prediction",
-                 clip_sample_range: float = 1.0, sample_max_value: float = 1.0, timestep_spacing: str = "trailing",
-                 rescale_betas_zero_snr: bool = True, snr_shift_scale: float = 1.0, **unused):
+                 beta_schedule: str = "scaled_linear", trained_betas=None, clip_sample: bool = True,
+                 set_alpha_to_one: bool = True, steps_offset: int = 0, prediction_type: str = "epsilon",
+                 clip_sample_range: float = 1.0, sample_max_value: float = 1.0, timestep_spacing: str = "leading",
+                 rescale_betas_zero_snr: bool = False, snr_shift_scale: float = 3.0, **unused):
         self.config = _Config(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
                               beta_schedule=beta_schedule, trained_betas=trained_betas, clip_sample=clip_sample,
                               set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset,
@@ -85,6 +100,25 @@ class CogVideoXDPMScheduler:
         cfg.update(kwargs)
         cfg.pop("variance_type", None)   # infer.py:283-287 forwards it; the DPM class has no use for it
         return cls(**{k: v for k, v in cfg.items() if not k.startswith("_")})
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, **kwargs):
+        """`infer.py:202`: CogVideoXDPMScheduler.from_pretrained(model_path, subfolder="scheduler") — reads
+        `<path>/<subfolder>/scheduler_config.json` (local directories only: there is no hub access here)."""
+        import json
+        import os
+
+        d = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        f = d if os.path.isfile(d) else os.path.join(d, cls.config_name)
+        if not os.path.isfile(f):
+            raise OSError(f"bya_b200: no {cls.config_name} under {d}")
+        with open(f, "r") as fh:
+            return cls.from_config(json.load(fh), **kwargs)
+
+    @classmethod
+    def cogvideox_5b(cls, **kwargs):
+        """The scheduler of the CogVideoX-5B lineage without a checkpoint directory at hand."""
+        return cls(**dict(COGVIDEOX_5B_SCHEDULER_CONFIG, **kwargs))
 
     def __len__(self):
         return self.config.num_train_timesteps

@@ -34,6 +34,8 @@ class PathConfig:
     audio_attn_interval: int = 1
     local_face_scale: float = 1.0
     batch: int = 1
+    use_rotary_positional_embeddings: bool = True
+    use_learned_positional_embeddings: bool = False   # CogVideoX-5B-I2V lineage: checkpoint key patch_embed.pos_embedding
 
     @property
     def dim(self) -> int:
@@ -58,7 +60,8 @@ class PathConfig:
             text_embed_dim=self.text_embed_dim, num_layers=self.num_layers, patch_size=self.patch_size,
             max_text_seq_length=self.text_len, sample_width=self.grid_w * self.patch_size,
             sample_height=self.grid_h * self.patch_size, sample_frames=4 * (self.frames - 1) + 1,
-            use_rotary_positional_embeddings=True, use_learned_positional_embeddings=False,
+            use_rotary_positional_embeddings=self.use_rotary_positional_embeddings,
+            use_learned_positional_embeddings=self.use_learned_positional_embeddings,
             is_train_face=True, cross_attn_interval=self.cross_attn_interval, local_face_scale=self.local_face_scale,
             is_train_audio=True, audio_attn_interval=self.audio_attn_interval,
         )
@@ -118,6 +121,13 @@ def fill_parameter(name: str, p: torch.Tensor, seed: int = 0) -> None:
 def fill_module(module: torch.nn.Module, seed: int = 0, prefix: str = "") -> None:
     for name, p in module.named_parameters():
         fill_parameter(prefix + name, p.data, seed)
+    # the LEARNED positional table is a persistent buffer (a checkpoint key): give it "trained" values, not the sincos init
+    persistent = set(module.state_dict().keys())
+    for name, b in module.named_buffers():
+        if name.endswith("patch_embed.pos_embedding") and name in persistent:
+            g = _gen(seed, prefix + name, b.device)
+            T = module.patch_embed.max_text_seq_length
+            b[:, T:].copy_(0.5 * torch.randn(b[:, T:].shape, generator=g, device=b.device, dtype=torch.float32))
 
 
 @torch.no_grad()
@@ -136,7 +146,8 @@ def make_inputs(cfg: PathConfig, seed: int = 1234, device="cpu", dtype=torch.flo
         hidden_states=rn(B, F, cfg.in_channels, H, W),
         encoder_hidden_states=rn(B, cfg.text_len, cfg.text_embed_dim, s=0.2),
         timestep=torch.full((B,), 500, dtype=torch.int64, device=device),
-        image_rotary_emb=tuple(t.to(device) for t in rope_3d_tables(cfg.attention_head_dim, cfg.frames, cfg.grid_h, cfg.grid_w)),
+        image_rotary_emb=tuple(t.to(device) for t in rope_3d_tables(cfg.attention_head_dim, cfg.frames, cfg.grid_h, cfg.grid_w))
+        if cfg.use_rotary_positional_embeddings else None,
         id_cond=[rn(B, 1280) for _ in range(C)],
         id_vit_hidden=[[rn(B, 577, 1024) for _ in range(5)] for _ in range(C)],
         audio_embeds=rn(B, C, cfg.audio_frames, 12, 768, s=0.27),

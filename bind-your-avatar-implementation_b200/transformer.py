@@ -93,15 +93,25 @@ class BindyouravatarTransformer3DModel(nn.Module):
         names = list(inspect.signature(self.__init__).parameters)
         self._config = _Config({k: frame.f_locals[k] for k in names})
         inner_dim = num_attention_heads * attention_head_dim
-        if not use_rotary_positional_embeddings:
-            raise NotImplementedError("bya_b200 implements the RoPE (CogVideoX-5B lineage) configuration only: pass "
-                                      "use_rotary_positional_embeddings=True (SURVEY.md §7)")
-        if use_learned_positional_embeddings:
-            raise NotImplementedError("bya_b200: learned positional embeddings are not implemented yet")
+        if not use_rotary_positional_embeddings and use_learned_positional_embeddings:
+            raise ValueError(   # same condition and wording as the reference (transformer.py:370-375)
+                "There are no CogVideoX checkpoints available with disable rotary embeddings and learned positional "
+                "embeddings. If you're using a custom model and/or believe this should be supported, please open an "
+                "issue at https://github.com/huggingface/diffusers/issues.")
+        if patch_size != 2:
+            raise NotImplementedError("bya_b200: the patchify / unpatchify kernels are built for patch_size == 2 "
+                                      "(every CogVideoX / ConsisID / Bind-Your-Avatar checkpoint)")
         if activation_fn != "gelu-approximate" or timestep_activation_fn != "silu" or flip_sin_to_cos is not True or freq_shift != 0:
             raise NotImplementedError("bya_b200: only the reference's activation / timestep-embedding configuration is built")
 
-        self.patch_embed = PatchEmbed(patch_size, in_channels, inner_dim, text_embed_dim)
+        self.patch_embed = PatchEmbed(patch_size, in_channels, inner_dim, text_embed_dim, sample_width=sample_width,
+                                      sample_height=sample_height, sample_frames=sample_frames,
+                                      temporal_compression_ratio=temporal_compression_ratio,
+                                      max_text_seq_length=max_text_seq_length,
+                                      spatial_interpolation_scale=spatial_interpolation_scale,
+                                      temporal_interpolation_scale=temporal_interpolation_scale,
+                                      use_positional_embeddings=not use_rotary_positional_embeddings,
+                                      use_learned_positional_embeddings=use_learned_positional_embeddings)
         self.time_embedding = TimestepEmbedding(inner_dim, time_embed_dim)
         self.transformer_blocks = nn.ModuleList([
             CogVideoXBlock(inner_dim, num_attention_heads, attention_head_dim, time_embed_dim, norm_elementwise_affine,
@@ -280,8 +290,6 @@ class BindyouravatarTransformer3DModel(nn.Module):
         if index_mask is not None or self.training and self.is_teacher_forcing:
             raise NotImplementedError("bya_b200 is the inference hot path; teacher forcing / router losses "
                                       "(transformer.py:741-774, :963-1021) are training-only and out of scope")
-        if image_rotary_emb is None:
-            raise NotImplementedError("bya_b200: image_rotary_emb is required (RoPE configuration)")
         if timestep_cond is not None:
             raise NotImplementedError("bya_b200: timestep_cond is not used by the reference pipeline")
         if not torch.is_tensor(timestep):
@@ -298,7 +306,7 @@ class BindyouravatarTransformer3DModel(nn.Module):
             audio_embeds, af_matrix = cfg_slice(audio_embeds, br), cfg_slice(af_matrix, br)
         eng = self.engine()
         if denoise_step == 0:
-            eng._prologue_key = None  # a new generation: recompute the timestep-invariant prologue
+            eng.new_generation()  # recompute the timestep-invariant prologue (eager cache and every captured graph)
         # (sequence parallel stays eager: capturing the NCCL all-to-alls hung on the 2-GPU box in round 1)
         if self.use_cuda_graph and taps is None and (self._sp_group is None or self.sp_cuda_graph):
             out = eng.step_graphed(hidden_states, encoder_hidden_states, timestep, image_rotary_emb, id_cond, id_vit_hidden,

@@ -62,8 +62,24 @@ class CogVideoXPatchEmbed(nn.Module):
         self.use_learned_positional_embeddings = use_learned_positional_embeddings
         self.proj = nn.Conv2d(in_channels, embed_dim, kernel_size=(patch_size, patch_size), stride=patch_size, bias=bias)
         self.text_proj = nn.Linear(text_embed_dim, embed_dim)
+        self.sample_height, self.sample_width, self.sample_frames = sample_height, sample_width, sample_frames
+        self.temporal_compression_ratio = temporal_compression_ratio
+        self.max_text_seq_length = max_text_seq_length
+        self.spatial_interpolation_scale = spatial_interpolation_scale
+        self.temporal_interpolation_scale = temporal_interpolation_scale
         if use_positional_embeddings or use_learned_positional_embeddings:
-            raise NotImplementedError("shim: only the RoPE configuration (5B lineage, SURVEY.md §7) is restated")
+            # sincos table; a PERSISTENT buffer (= checkpoint key `patch_embed.pos_embedding`) only when learned
+            pos = self._get_positional_embeddings(sample_height, sample_width, sample_frames)
+            self.register_buffer("pos_embedding", pos, persistent=use_learned_positional_embeddings)
+
+    def _get_positional_embeddings(self, sample_height, sample_width, sample_frames, device=None):
+        ph, pw = sample_height // self.patch_size, sample_width // self.patch_size
+        pf = (sample_frames - 1) // self.temporal_compression_ratio + 1
+        pos = get_3d_sincos_pos_embed(self.embed_dim, (pw, ph), pf, self.spatial_interpolation_scale,
+                                      self.temporal_interpolation_scale, device=device).flatten(0, 1)
+        joint = pos.new_zeros(1, self.max_text_seq_length + ph * pw * pf, self.embed_dim)
+        joint[:, self.max_text_seq_length:].copy_(pos)
+        return joint
 
     def forward(self, text_embeds, image_embeds):
         text_embeds = self.text_proj(text_embeds)
@@ -73,7 +89,52 @@ class CogVideoXPatchEmbed(nn.Module):
         x = x.view(b, f, *x.shape[1:])
         x = x.flatten(3).transpose(2, 3)  # [b, f, h*w, D]
         x = x.flatten(1, 2)  # [b, f*h*w, D]
-        return torch.cat([text_embeds, x], dim=1).contiguous()
+        embeds = torch.cat([text_embeds, x], dim=1).contiguous()
+        if self.use_positional_embeddings or self.use_learned_positional_embeddings:
+            if self.use_learned_positional_embeddings and (self.sample_width != w or self.sample_height != h):
+                raise ValueError("It is currently not possible to generate videos at a different resolution that the "
+                                 "defaults. This should only be the case with 'THUDM/CogVideoX-5b-I2V'.")
+            pre_frames = (f - 1) * self.temporal_compression_ratio + 1
+            if self.sample_height != h or self.sample_width != w or self.sample_frames != pre_frames:
+                pos = self._get_positional_embeddings(h, w, pre_frames, device=embeds.device)
+            else:
+                pos = self.pos_embedding
+            embeds = embeds + pos.to(dtype=embeds.dtype)
+        return embeds
+
+
+def get_1d_sincos_pos_embed_from_grid(embed_dim, pos):
+    omega = torch.arange(embed_dim // 2, device=pos.device, dtype=torch.float64)
+    omega /= embed_dim / 2.0
+    omega = 1.0 / 10000 ** omega
+    out = torch.outer(pos.reshape(-1), omega)
+    return torch.concat([torch.sin(out), torch.cos(out)], dim=1)
+
+
+def get_2d_sincos_pos_embed_from_grid(embed_dim, grid):
+    emb_h = get_1d_sincos_pos_embed_from_grid(embed_dim // 2, grid[0])
+    emb_w = get_1d_sincos_pos_embed_from_grid(embed_dim // 2, grid[1])
+    return torch.concat([emb_h, emb_w], dim=1)
+
+
+def get_3d_sincos_pos_embed(embed_dim, spatial_size, temporal_size, spatial_interpolation_scale=1.0,
+                            temporal_interpolation_scale=1.0, device=None):
+    """Published diffusers algorithm: [T, H*W, D] = [temporal D/4 | spatial 3D/4 (first half from the w-grid, second
+    from the h-grid: meshgrid(grid_w, grid_h, indexing='xy'))], each half [sin | cos]."""
+    assert embed_dim % 4 == 0
+    if isinstance(spatial_size, int):
+        spatial_size = (spatial_size, spatial_size)
+    d_sp, d_t = 3 * embed_dim // 4, embed_dim // 4
+    grid_h = torch.arange(spatial_size[1], device=device, dtype=torch.float32) / spatial_interpolation_scale
+    grid_w = torch.arange(spatial_size[0], device=device, dtype=torch.float32) / spatial_interpolation_scale
+    grid = torch.stack(torch.meshgrid(grid_w, grid_h, indexing="xy"), dim=0)
+    grid = grid.reshape([2, 1, spatial_size[1], spatial_size[0]])
+    pos_sp = get_2d_sincos_pos_embed_from_grid(d_sp, grid)
+    grid_t = torch.arange(temporal_size, device=device, dtype=torch.float32) / temporal_interpolation_scale
+    pos_t = get_1d_sincos_pos_embed_from_grid(d_t, grid_t)
+    pos_sp = pos_sp[None].repeat_interleave(temporal_size, dim=0)
+    pos_t = pos_t[:, None].repeat_interleave(spatial_size[0] * spatial_size[1], dim=1)
+    return torch.concat([pos_t, pos_sp], dim=-1).float()
 
 
 def get_1d_rotary_pos_embed(dim, pos, theta=10000.0, use_real=True):

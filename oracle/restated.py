@@ -40,7 +40,22 @@ def _heads(x, h):  # [b, n, h*d] -> [b, h, n, d]
 
 
 def _sdpa(q, k, v):
-    return F.scaled_dot_product_attention(q, k, v)
+    """softmax(q k^T / sqrt(d)) v.  Small problems go through torch's SDPA; large fp32 ones (the full 17 776-token grid
+    on the GPU) are evaluated explicitly a few heads at a time, so the truth never depends on which fused backend
+    torch would pick for fp32 and never materialises more than ~6 GB of scores."""
+    n_q, n_k = q.shape[-2], k.shape[-2]
+    if q.dtype != torch.float32 or not q.is_cuda or q.shape[:-2].numel() * n_q * n_k * 4 <= (2 << 30):
+        return F.scaled_dot_product_attention(q, k, v)
+    lead = q.shape[:-2]
+    q2, k2, v2 = (t.reshape(-1, t.shape[-2], t.shape[-1]) for t in (q.expand(*lead, -1, -1), k.expand(*lead, -1, -1), v.expand(*lead, -1, -1)))
+    out = torch.empty(q2.shape[0], n_q, v2.shape[-1], device=q.device, dtype=q.dtype)
+    step = max(1, int((6 << 30) // (n_q * n_k * 4)))
+    scale = q.shape[-1] ** -0.5
+    for i in range(0, q2.shape[0], step):
+        w = torch.bmm(q2[i:i + step] * scale, k2[i:i + step].transpose(1, 2))
+        out[i:i + step] = torch.softmax(w, dim=-1) @ v2[i:i + step]
+        del w
+    return out.reshape(*lead, n_q, v2.shape[-1])
 
 
 def rope_rotate(x, cos, sin):
@@ -64,6 +79,26 @@ def patch_embed(sd, text, latents, p):
     x = F.conv2d(latents.reshape(-1, c, h, w), sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=p)
     x = x.view(b, f, x.shape[1], -1).transpose(2, 3).flatten(1, 2)  # [b, f*gh*gw, D], (f,h,w) row-major
     return _lin(sd, "patch_embed.text_proj", text), x
+
+
+def positional_table(sd, cfg, frames, gh, gw):
+    """The joint table diffusers' CogVideoXPatchEmbed adds after the patch embedding (reference ctor
+    models/transformer.py:370-392): the checkpoint buffer when learned (CogVideoX-5B-I2V lineage), the analytic sincos
+    table when the model is built without RoPE, nothing for the RoPE-only configuration."""
+    if getattr(cfg, "use_learned_positional_embeddings", False):
+        return sd["patch_embed.pos_embedding"]
+    if getattr(cfg, "use_rotary_positional_embeddings", True):
+        return None
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "_bya_shim_embeddings", os.path.join(os.path.dirname(os.path.abspath(__file__)), "diffusers_shim", "diffusers",
+                                             "models", "embeddings.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pos = mod.get_3d_sincos_pos_embed(cfg.dim, (gw, gh), frames, 1.875, 1.0).flatten(0, 1)
+    return torch.cat([torch.zeros(cfg.text_len, cfg.dim), pos], 0)[None]
 
 
 # ----------------------------------------------------------------------------- DiT block
@@ -292,7 +327,8 @@ def step(sd: Dict[str, torch.Tensor], cfg, hidden_states, encoder_hidden_states,
     p, C, heads = cfg.patch_size, cfg.chars, cfg.num_attention_heads
     gh, gw = Hl // p, Wl // p
     dtype = hidden_states.dtype
-    tap = (lambda k, v: taps.__setitem__(k, v.detach().float().cpu())) if taps is not None else (lambda k, v: None)
+    tap = taps if callable(taps) else (
+        (lambda k, v: taps.__setitem__(k, v.detach().float().cpu())) if taps is not None else (lambda k, v: None))
 
     face = torch.stack([facial_extractor(sd, id_cond[c], id_vit_hidden[c]) for c in range(C)], 1)  # [B,C,32,2048]
     tap("face_tokens", face)
@@ -305,6 +341,10 @@ def step(sd: Dict[str, torch.Tensor], cfg, hidden_states, encoder_hidden_states,
     temb = time_embedding(sd, timestep, cfg.dim, dtype)
     tap("temb", temb)
     e, h = patch_embed(sd, encoder_hidden_states, hidden_states, p)
+    pos = positional_table(sd, cfg, Fr, gh, gw)
+    if pos is not None:
+        pos = pos.to(h.device, h.dtype)
+        e, h = e + pos[:, :e.shape[1]], h + pos[:, e.shape[1]:]
     tap("embed_video", h)
     routing = [torch.zeros(1, h.shape[1], C, dtype=dtype, device=h.device) for _ in range(B)]
     ca = 0

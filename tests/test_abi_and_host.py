@@ -203,6 +203,46 @@ def test_checkpoint_round_trip_through_the_reference_loaders(tmp_path):
             assert torch.equal(out[k], v), k
 
 
+def test_i2v_style_checkpoint_with_learned_positional_table_round_trips(tmp_path):
+    """the CogVideoX-5B-I2V lineage the real checkpoint descends from ships
+    `use_learned_positional_embeddings: true` in config.json and a `patch_embed.pos_embedding` tensor
+    [1, text + patches, dim] in the safetensors (models/transformer.py:370-392, :1024-1093).  The drop-in must build from
+    that config, take the table from the file, and refuse what the reference refuses."""
+    from safetensors.torch import save_file
+
+    import bya_b200  # noqa: F401
+    from bya_b200.synth import fill_module
+    from bya_b200.transformer import BindyouravatarTransformer3DModel as M
+
+    kw = dict(num_attention_heads=2, attention_head_dim=64, in_channels=32, out_channels=16, num_layers=1,
+              text_embed_dim=64, time_embed_dim=32, sample_width=12, sample_height=8, sample_frames=9,
+              max_text_seq_length=10, use_rotary_positional_embeddings=True, use_learned_positional_embeddings=True)
+    src = M(**kw, is_train_face=False).eval()
+    fill_module(src, 5)
+    sd = src.state_dict()
+    assert tuple(sd["patch_embed.pos_embedding"].shape) == (1, 10 + 3 * 4 * 6, 128)
+    assert float(sd["patch_embed.pos_embedding"][:, :10].abs().max()) == 0.0      # text rows carry no position
+    d = tmp_path / "transformer"
+    d.mkdir()
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(d / "diffusion_pytorch_model.safetensors"))
+    (d / "config.json").write_text(json.dumps(kw))
+    dst = M.from_pretrained_cus(str(tmp_path), subfolder="transformer", transformer_additional_kwargs=dict(is_train_face=False))
+    assert dst.config.use_learned_positional_embeddings is True
+    out = dst.state_dict()
+    assert set(out) == set(sd) and all(torch.equal(out[k], sd[k]) for k in sd)
+    assert dst.patch_embed.table_for(3, 8, 12) is dst.patch_embed.pos_embedding
+    with pytest.raises(ValueError):        # the learned table cannot be re-derived for another resolution
+        dst.patch_embed.table_for(3, 8, 16)
+    # non-RoPE construction: analytic sincos table, NOT a checkpoint key; other geometries are re-derived
+    plain = M(**dict(kw, use_rotary_positional_embeddings=False, use_learned_positional_embeddings=False), is_train_face=False)
+    assert "patch_embed.pos_embedding" not in plain.state_dict()
+    assert tuple(plain.patch_embed.table_for(5, 8, 16).shape) == (1, 10 + 5 * 4 * 8, 128)
+    with pytest.raises(ValueError):        # same refusal, same condition as transformer.py:370-375
+        M(**dict(kw, use_rotary_positional_embeddings=False))
+    with pytest.raises(NotImplementedError):
+        M(**dict(kw, patch_size=4))
+
+
 def test_ctypes_structs_match_the_c_header_layout(tmp_path):
     """`include/bya.h` is plain C: compile a probe with gcc that prints sizeof / offsetof of every field of the two
     argument structs and compare with the ctypes mirrors in `bya_b200/lib.py` (a drifted field would silently shift

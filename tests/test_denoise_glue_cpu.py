@@ -15,7 +15,7 @@ def sched():
     import bya_b200  # noqa: F401
     from bya_b200.scheduler import CogVideoXDPMScheduler
 
-    return CogVideoXDPMScheduler   # CogVideoX-5B scheduler_config.json values are the constructor defaults
+    return CogVideoXDPMScheduler.cogvideox_5b   # the CogVideoX-5B scheduler_config.json values (ctor defaults are diffusers')
 
 
 def test_trailing_timesteps_and_zero_terminal_snr(sched):
@@ -34,11 +34,26 @@ def test_trailing_timesteps_and_zero_terminal_snr(sched):
         s.set_timesteps(1001)
 
 
-def test_from_config_drops_variance_type_like_infer_py(sched):
-    s = sched.from_config(dict(sched().config), variance_type="fixed_small", snr_shift_scale=3.0)
+def test_from_config_drops_variance_type_like_infer_py(sched, tmp_path):
+    import json
+
+    from bya_b200.scheduler import COGVIDEOX_5B_SCHEDULER_CONFIG, CogVideoXDPMScheduler
+
+    s = CogVideoXDPMScheduler.from_config(dict(sched().config), variance_type="fixed_small", snr_shift_scale=3.0)
     assert s.config.snr_shift_scale == 3.0 and "variance_type" not in s.config
     with pytest.raises(ValueError):
         sched(prediction_type="flow")
+    # bare constructor = the published class's defaults, not the 5B checkpoint's values
+    d = CogVideoXDPMScheduler().config
+    assert (d.prediction_type, d.timestep_spacing, d.rescale_betas_zero_snr, d.snr_shift_scale) == ("epsilon", "leading", False, 3.0)
+    # infer.py:202: CogVideoXDPMScheduler.from_pretrained(model_path, subfolder="scheduler")
+    (tmp_path / "scheduler").mkdir()
+    cfg = dict(COGVIDEOX_5B_SCHEDULER_CONFIG, _class_name="CogVideoXDPMScheduler", _diffusers_version="0.30.0.dev0")
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(cfg))
+    p = CogVideoXDPMScheduler.from_pretrained(str(tmp_path), subfolder="scheduler")
+    assert dict(p.config) == dict(sched().config)
+    with pytest.raises(OSError):
+        CogVideoXDPMScheduler.from_pretrained(str(tmp_path), subfolder="nope")
 
 
 @pytest.mark.parametrize("steps,shift", [(50, 1.0), (50, 3.0), (12, 1.0), (1000, 1.0)])
@@ -128,7 +143,7 @@ def test_dynamic_guidance_matches_pipeline_formula():
     from bya_b200.scheduler import CogVideoXDPMScheduler
     from oracle.dpm_oracle import dynamic_guidance
 
-    s = CogVideoXDPMScheduler()
+    s = CogVideoXDPMScheduler.cogvideox_5b()
     s.set_timesteps(50)
     loop = DenoiseLoop(None, s, guidance_scale=6.0, use_dynamic_cfg=True)
     tab = loop.coefficient_table(50)
@@ -149,7 +164,7 @@ def test_up_front_noise_draws_follow_the_reference_order():
     from oracle.dpm_oracle import DPMSchedulerOracle, denoise_loop_oracle
 
     shape, steps = (1, 2, 16, 4, 6), 7
-    sch = CogVideoXDPMScheduler()
+    sch = CogVideoXDPMScheduler.cogvideox_5b()
     sch.set_timesteps(steps)
     loop = DenoiseLoop(None, sch, guidance_scale=3.0)
     noise = loop.draw_noise(shape, loop.coefficient_table(steps), torch.Generator().manual_seed(21), "cpu")

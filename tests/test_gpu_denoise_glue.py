@@ -122,7 +122,7 @@ def test_scheduler_step_drop_in_same_seed_same_latents(built):
     from bya_b200.scheduler import CogVideoXDPMScheduler
     from oracle.dpm_oracle import DPMSchedulerOracle
 
-    sch, orc = CogVideoXDPMScheduler(), DPMSchedulerOracle()
+    sch, orc = CogVideoXDPMScheduler.cogvideox_5b(), DPMSchedulerOracle()
     sch.set_timesteps(5, device="cuda")
     orc.set_timesteps(5)
     assert sch.timesteps.is_cuda
@@ -164,7 +164,7 @@ def test_denoise_loop_graph_equals_eager_equals_pipeline_oracle(built, zero2cond
     common = dict(prompt_embeds=inp["encoder_hidden_states"], image_rotary_emb=inp["image_rotary_emb"],
                   id_cond=inp["id_cond"], id_vit_hidden=inp["id_vit_hidden"], audio_embeds=inp["audio_embeds"],
                   af_matrix=inp["af_matrix"], num_inference_steps=steps)
-    mk = lambda graph: DenoiseLoop(m, CogVideoXDPMScheduler(), guidance_scale=guidance, use_dynamic_cfg=dynamic,
+    mk = lambda graph: DenoiseLoop(m, CogVideoXDPMScheduler.cogvideox_5b(), guidance_scale=guidance, use_dynamic_cfg=dynamic,
                                    zero2cond_cfg_flag=zero2cond, cuda_graph=graph)
     # eager kernels, with a per-step trace, drawing from a seeded device generator
     trace = []
@@ -221,7 +221,7 @@ def test_denoise_loop_batches_the_conditions_like_the_pipeline(built):
         conds = (inp["id_cond"], inp["id_vit_hidden"], inp["audio_embeds"], inp["af_matrix"])
         if batched:
             conds = prepare_cfg_conditions(*conds, True, True)
-        loop = DenoiseLoop(m, CogVideoXDPMScheduler(), guidance_scale=4.0, zero2cond_cfg_flag=True)
+        loop = DenoiseLoop(m, CogVideoXDPMScheduler.cogvideox_5b(), guidance_scale=4.0, zero2cond_cfg_flag=True)
         outs.append(loop.run(lat, img, bg, prompt, inp["image_rotary_emb"], *conds, num_inference_steps=3,
                              generator=torch.Generator(device="cuda").manual_seed(9),
                              conditions_cfg_batched=batched).clone())

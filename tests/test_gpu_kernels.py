@@ -100,6 +100,107 @@ def test_gemm_qkv_layernorm_rope(ops):
     assert rel(out, ref) < 1.5e-2
 
 
+def _gemm_ref_sampled(a, w, rows, cols):
+    """fp32 reference on a sample of output rows / columns (the full product of the hot shapes is 0.7-1.3 TFLOP)."""
+    return a[rows].float() @ w[cols].float().t()
+
+
+@pytest.mark.parametrize("M,N,K,act", [(17776, 9216, 3072, 0), (17776, 12288, 3072, 1), (17776, 3072, 12288, 0),
+                                       (17776, 3072, 3072, 0), (17550, 2048, 3072, 0), (35100, 1536, 512, 0),
+                                       (4444, 9216, 3072, 0), (2222, 3072, 12288, 0)])
+def test_gemm_hot_shapes(ops, M, N, K, act):
+    """The step's own GEMM shapes at configs[1] (QKV, FFN-in + GELU, FFN-out, attention out, face to_q, router QKV) and the
+    per-rank row counts of 4- and 8-way sequence parallelism; every output row block and column block is sampled."""
+    torch.manual_seed(21)
+    a, w, b = rnd(M, K, s=0.5), rnd(N, K, s=0.03), rnd(N, s=0.1)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, bias=b, act=act)
+    rows = torch.cat([torch.arange(0, M, 61, device=dev), torch.arange(max(M - 130, 0), M, device=dev)])
+    ref = a[rows].float() @ w.float().t() + b.float()
+    ref = F.gelu(ref, approximate="tanh") if act == 1 else ref
+    assert rel(out[rows], ref) < TOL
+    assert torch.isfinite(out.float()).all()
+
+
+def test_gemm_hot_shape_gated_residual_in_place(ops):
+    """FFN-out at full size exactly as the engine calls it: K = 12 288, in-place gated residual, text / video gate split."""
+    torch.manual_seed(22)
+    M, N, K, split = 17776, 3072, 12288, 226
+    a, w, b, h = rnd(M, K, s=0.3), rnd(N, K, s=0.02), rnd(N, s=0.1), rnd(M, N)
+    ga, gb = torch.randn(N, device=dev), torch.randn(N, device=dev)
+    out = h.clone()
+    ops.gemm(a, w, out, bias=b, mode=ops.EPI_RESIDUAL, resid=out, gate_a=ga, gate_b=gb, split_row=split)
+    rows = torch.cat([torch.arange(0, 400, device=dev), torch.arange(400, M, 53, device=dev)])
+    gate = torch.where((rows < split)[:, None], ga[None], gb[None])
+    ref = h[rows].float() + gate * (a[rows].float() @ w.float().t() + b.float()[None])
+    assert rel(out[rows], ref) < TOL
+
+
+@pytest.mark.parametrize("P,R", [(2, 1000), (4, 4444), (8, 2222)])
+def test_gemm_col_block_and_a_kblock(ops, P, R):
+    """The two layouts of the sequence-parallel exchange (engine.py): `col_block` = the QKV GEMM writes
+    the all-to-all send buffer [dest][row][cols of dest] through a 3-D TMA store map (with the qk-LayerNorm / RoPE
+    epilogue on destination-ordered weight rows); `a_kblock` = the out-projection reads the receive buffer
+    [src][row][cols of src] as a K-blocked A operand.  Both against the plain layout of the same GEMM."""
+    from bya_b200.sp import qkv_rows_by_destination
+
+    torch.manual_seed(23)
+    D, K, T = 1536, 1024, 226        # 24 heads
+    Dl = D // P
+    a, w, b = rnd(R, K, s=0.5), rnd(3 * D, K, s=0.05), rnd(3 * D, s=0.1)
+    nq = [(1 + 0.1 * torch.randn(64, device=dev)).bfloat16(), (0.1 * torch.randn(64, device=dev)).bfloat16()]
+    nk = [(1 + 0.1 * torch.randn(64, device=dev)).bfloat16(), (0.1 * torch.randn(64, device=dev)).bfloat16()]
+    ang = torch.rand(R + 77, 32, device=dev) * 6.28
+    cos, sin = ang.cos().repeat_interleave(2, 1).contiguous(), ang.sin().repeat_interleave(2, 1).contiguous()
+    plain = torch.empty(R, 3 * D, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, plain, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos, sin), rope_row0=77, nq=nq, nk=nk,
+             q_premul=0.18)
+    send = torch.full((P, R, 3 * Dl), 9.0, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, qkv_rows_by_destination(w, D, P), send[0], bias=qkv_rows_by_destination(b, D, P), mode=ops.EPI_QKV,
+             split_row=T, ln_eps=1e-6, rope=(cos, sin), rope_row0=77, nq=nq, nk=nk, qkv_block=3 * Dl, col_block=3 * Dl,
+             col_block_stride=R * 3 * Dl, q_premul=0.18)
+    for d in range(P):   # destination d receives [q | k | v] of its heads: bit-identical to the plain layout's columns
+        want = torch.cat([plain[:, j * D + d * Dl: j * D + (d + 1) * Dl] for j in range(3)], 1)
+        assert torch.equal(send[d], want), d
+    # K-blocked A: recv [P][R][Dl] holds column block s of the logical [R, D] operand
+    x = rnd(R, D, s=0.5)
+    wo, bo, h = rnd(K, D, s=0.05), rnd(K, s=0.1), rnd(R, K)
+    g = torch.randn(K, device=dev)
+    recv = x.view(R, P, Dl).permute(1, 0, 2).contiguous()
+    o1, o2 = h.clone(), h.clone()
+    ops.gemm(x, wo, o1, bias=bo, mode=ops.EPI_RESIDUAL, resid=o1, gate_a=g, gate_b=g)
+    ops.gemm(recv[0], wo, o2, bias=bo, mode=ops.EPI_RESIDUAL, resid=o2, gate_a=g, gate_b=g, a_kblock=Dl, a_kblock_stride=R * Dl)
+    assert torch.equal(o1, o2)
+    assert rel(o1, h.float() + g * (x.float() @ wo.float().t() + bo.float())) < TOL
+
+
+def test_attention_d64_full_sequence_48_heads(ops):
+    """The joint self-attention at its real size (17 776 tokens x 48 heads, bounded-score kernel, q pre-scaled as the
+    QKV epilogue leaves it) vs fp32 math on sampled heads and query rows; the general kernel on the same inputs."""
+    torch.manual_seed(24)
+    seq, heads = 17776, 48
+    D = heads * 64
+    x = torch.randn(seq, 3 * heads, 64, device=dev)
+    x[:, :2 * heads] = F.layer_norm(x[:, :2 * heads], (64,)) * 1.2
+    x[:, :heads] *= 0.125 * 1.4426950408889634
+    qkv = x.reshape(seq, 3 * D).bfloat16()
+    del x
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    bound = 1.02 * (8 * 1.2) ** 2 * 0.125 * 1.4426950408889634
+    out = torch.zeros(seq, D, device=dev, dtype=torch.bfloat16)
+    ops.attention_d64(q, k, v, out, 1, seq, heads, score_bound_log2=bound)
+    out2 = torch.zeros_like(out)
+    ops.attention_d64(q, k, v, out2, 1, seq, heads, scale=math.log(2.0))
+    rows = torch.cat([torch.arange(0, seq, 97, device=dev), torch.arange(seq - 160, seq, device=dev)])
+    for h in (0, 1, 17, 31, 47):
+        sl = slice(h * 64, (h + 1) * 64)
+        p = torch.softmax(q[rows, sl].float() @ k[:, sl].float().t() * math.log(2.0), -1)
+        ref = p @ v[:, sl].float()
+        assert rel(out[rows, sl], ref) < TOL, h
+        assert rel(out2[rows, sl], ref) < TOL, h
+    assert torch.isfinite(out.float()).all()
+
+
 def test_gemm_rejects_bad_shapes(ops):
     a = rnd(128, 100)
     with pytest.raises(RuntimeError):

@@ -40,6 +40,65 @@ def test_restated_oracle_matches_reference_golden_config1(c1_model_state):
     assert float((taps["face_tokens"][:, :, ::4] - g["face_tokens"]).abs().max()) < 1e-4
 
 
+def _cpu_model_state(cfg):
+    import bya_b200  # noqa: F401
+    from bya_b200.synth import fill_module
+    from bya_b200.transformer import BindyouravatarTransformer3DModel
+
+    m = BindyouravatarTransformer3DModel(**cfg.ctor_kwargs()).eval()
+    m.router.set_grid(cfg.frames, cfg.grid_h, cfg.grid_w)
+    fill_module(m, 0)
+    return m, dict(m.state_dict())
+
+
+def test_restated_oracle_matches_reference_golden_L4_interval2_batch2():
+    """tests/golden/step_L4_int2_b2.pt (UNMODIFIED reference, round 2): 4 blocks, cross_attn_interval=2 — layers 1 and 3
+    take the audio weights from the routing of the PREVIOUS cross-attention layer (transformer.py:858-863) — CFG batch 2
+    with the unconditional branch's audio zeroed.  Pins the layer loop, not just one block."""
+    import dataclasses
+
+    from bya_b200.synth import CONFIGS, make_inputs
+    from oracle import restated
+
+    cfg = dataclasses.replace(CONFIGS["c1"], num_layers=4, cross_attn_interval=2, batch=2)
+    _, sd = _cpu_model_state(cfg)
+    g = torch.load(os.path.join(GOLD, "step_L4_int2_b2.pt"))
+    inp = make_inputs(cfg, g["input_seed"])
+    inp["audio_embeds"][0] = 0
+    taps = {}
+    out = restated.step(sd, cfg, **inp, taps=taps)
+    assert float((out - g["output"]).abs().max()) < 5e-4
+    for i in range(4):
+        assert float((taps[f"block{i}.video"][:, ::13, ::7] - g[f"block{i}.video"]).abs().max()) < 2e-4, i
+    # router calls of the reference: [ca0 b0, ca0 b1, ca1 b0, ca1 b1]; the oracle taps batch element 0
+    assert float((taps["ca0.router"] - g["router"][0]).abs().max()) < 1e-5
+    assert float((taps["ca1.router"] - g["router"][2]).abs().max()) < 1e-5
+    assert "ca2.router" not in taps
+
+
+@pytest.mark.parametrize("name,kw", [("step_c1_learnedpos.pt", dict(use_learned_positional_embeddings=True)),
+                                     ("step_c1_sincos.pt", dict(use_rotary_positional_embeddings=False))])
+def test_positional_embedding_configurations_vs_reference_golden(name, kw):
+    """The two other constructions of the reference's patch embedding (models/transformer.py:370-392): the learned
+    `patch_embed.pos_embedding` checkpoint buffer of the CogVideoX-5B-I2V lineage (with RoPE), and the analytic sincos
+    table of a model built without RoPE.  Goldens by the UNMODIFIED reference on the diffusers shim; the product-side
+    table (`bya_b200.modules.sincos_positional_embedding`) must equal the shim's."""
+    import dataclasses
+
+    from bya_b200.synth import CONFIGS, make_inputs
+    from oracle import restated
+
+    cfg = dataclasses.replace(CONFIGS["c1"], **kw)
+    m, sd = _cpu_model_state(cfg)
+    assert ("patch_embed.pos_embedding" in sd) == bool(kw.get("use_learned_positional_embeddings"))
+    g = torch.load(os.path.join(GOLD, name))
+    assert float((m.patch_embed.pos_embedding[:, ::61, ::17] - g["pos_embedding_sub"]).abs().max()) < 1e-6
+    inp = make_inputs(cfg, g["input_seed"])
+    assert (inp["image_rotary_emb"] is None) == (not cfg.use_rotary_positional_embeddings)
+    out = restated.step(sd, cfg, **inp)
+    assert float((out - g["output"]).abs().max()) < 2e-4
+
+
 def test_restated_oracle_generalises_consistently(c1_model_state):
     """C>2 audio-weight rule reduces to the reference's swap at C=2; frame-OR matches transformer.py:815-818."""
     from oracle import restated

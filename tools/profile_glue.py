@@ -15,7 +15,7 @@ from bya_b200.scheduler import CogVideoXDPMScheduler  # noqa: E402
 F, C, H, W, B = 13, 16, 60, 90, 2
 n = F * C * H * W
 dev = "cuda"
-sch = CogVideoXDPMScheduler()
+sch = CogVideoXDPMScheduler.cogvideox_5b()
 sch.set_timesteps(50)
 ts = sch.timesteps.tolist()
 coef = torch.tensor([sch.step_coefficients(t, ts[i - 1] if i else None, i > 0, 6.0) for i, t in enumerate(ts)],
