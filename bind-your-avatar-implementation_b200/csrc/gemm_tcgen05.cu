@@ -1,5 +1,13 @@
 // C[M,N] = epilogue(A[M,K] · W[N,K]^T)   bf16 in, fp32 accumulate in TMEM, bf16 out.   sm_100a only.
 //
+// Two builds of one kernel template:
+//   CTAS = 2 (default for the step's large GEMMs): a CTA PAIR (cluster of 2 = the two SMs of a TPC) owns a 256 x 256
+//            output tile and runs tcgen05.mma.cta_group::2 with M = 256: each CTA stages its own 128 rows of A and only
+//            HALF of the B tile (128 of the 256 weight rows) per k-block — 32 KB per stage instead of 48 KB, so 6
+//            stages fit, the B operand crosses L2 -> SM once per pair, and shared-memory read traffic per MMA halves.
+//            Only the even CTA issues MMAs; its barriers collect the peer's TMA bytes (.cta_group::2 loads) and the
+//            peer's epilogue arrivals (remote mbarrier.arrive); tcgen05.commit multicasts to both CTAs.
+//   CTAS = 1: one CTA per 128 x BN tile (small M, BN < 256, or BYA_GEMM_CTAS=1).
 // One persistent CTA per SM, warp-specialised:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled tiles, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM)
@@ -24,14 +32,15 @@ namespace bya {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kStages = 4;
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
 
-template <int BN>
+template <int BN, int CTAS>
 struct GemmSmem {
+  static constexpr int kStages = CTAS == 2 ? 6 : 4;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBRows = BN / CTAS;            // weight rows staged by ONE CTA per k-block
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiOffset = kStages * kStageBytes;          // [2 stages][bias | gate_a | gate_b][BN] fp32
   static constexpr int kEpiBytes = 2 * 3 * BN * 4;
@@ -48,13 +57,18 @@ __device__ long long* g_gemm_trace = nullptr;
     if (g_gemm_trace && blockIdx.x == 0 && (i) < 16 && lane == 0) g_gemm_trace[(i) * 8 + (e)] = clock64(); \
   } while (0)
 
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  using L = GemmSmem<BN>;
+  using L = GemmSmem<BN, CTAS>;
+  constexpr int kStages = L::kStages;
+  constexpr int TM = BM * CTAS;                         // output rows per tile (per CTA pair when CTAS = 2)
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+  const int unit = CTAS == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);   // scheduler unit: CTA or CTA pair
+  const int num_units = int(gridDim.x) / CTAS;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
@@ -63,7 +77,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (p.M + BM - 1) / BM;
+  const int num_m = (p.M + TM - 1) / TM;
   const int num_n = p.N / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = p.K / BK;
@@ -81,13 +95,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiThreads);
+      mbar_init(&tempty_bar[s], kEpiThreads * CTAS);   // the leader's copy also collects the peer's epilogue
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (CTAS == 2) tmem_alloc_pair<kTmemCols>(tmem_slot);
+    else tmem_alloc<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // the peer's barriers exist before anything is signalled across
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -110,36 +128,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int ti = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+      for (int t = unit; t < num_tiles; t += num_units, ++ti) {
         int mb, nb;
         tile_coord(t, mb, nb);
+        const int arow = mb * TM + int(rank) * BM;             // this CTA's 128 rows of A
+        const int brow = nb * BN + int(rank) * L::kBRows;      // this CTA's share of the weight rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (kb == 0) GEMM_TRACE(0, ti);
           if (kb == num_kb - 1) GEMM_TRACE(1, ti);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          if (p.a_kblock) {
-            const int k0 = kb * BK;
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], k0 % p.a_kblock, mb * BM, k0 / p.a_kblock, kEvictNormal);
+          if constexpr (CTAS == 2) {
+            // the LEADER's barrier collects the bytes of both CTAs' loads of this stage
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes * 2);
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (p.a_kblock) {
+              const int k0 = kb * BK;
+              tma_load_3d_pair(sa, &tmap_a, bar, k0 % p.a_kblock, arow, k0 / p.a_kblock, kEvictNormal);
+            } else {
+              tma_load_2d_pair(sa, &tmap_a, bar, kb * BK, arow, kEvictNormal);
+            }
+            tma_load_2d_pair(sb, &tmap_b, bar, kb * BK, brow, kEvictLast);
           } else {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, mb * BM, kEvictNormal);
+            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            if (p.a_kblock) {
+              const int k0 = kb * BK;
+              tma_load_3d(sa, &tmap_a, &full_bar[stage], k0 % p.a_kblock, arow, k0 / p.a_kblock, kEvictNormal);
+            } else {
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, arow, kEvictNormal);
+            }
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, brow, kEvictLast);
           }
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, nb * BN, kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (the leader CTA of a pair)
+    constexpr uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
     int ti = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+    for (int t = unit; t < num_tiles; t += num_units, ++ti) {
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       GEMM_TRACE(2, ti);
       tc_fence_after();
@@ -156,10 +189,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t db = make_smem_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_ss(tmem_acc, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_ss_pair(tmem_acc, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0);
+            else umma_ss(tmem_acc, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+          if constexpr (CTAS == 2) {   // both CTAs' producers / epilogues are released by the same completion
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[as]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -175,10 +214,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     int ti = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+    const uint32_t tempty_leader = CTAS == 2 ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
+    for (int t = unit; t < num_tiles; t += num_units, ++ti) {
       int mb, nb;
       tile_coord(t, mb, nb);
       const int col0 = nb * BN;
+      const int trow0 = mb * TM + int(rank) * BM;   // first output row of this CTA's half of the tile
       if (warp == 4) GEMM_TRACE(5, ti);
       // stage this tile's column vectors while the main loop is still running
       float* sbias = epi + as * 3 * BN;
@@ -195,7 +236,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&tfull_bar[as], aphase);
       if (warp == 4) GEMM_TRACE(6, ti);
       tc_fence_after();
-      const int row = mb * BM + q * 32 + lane;
+      const int row = trow0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + as * BN + (uint32_t(q * 32) << 16);
       // Output: 32 rows x 32 columns per warp and chunk -> shared memory (64B-swizzled, conflict-free 16 B stores)
@@ -205,7 +246,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // buffer) the map is 3-D [dest][row][col].
       uint8_t* stg = smem + L::kStgOffset + (warp - 4) * 2048;
       const uint32_t stg_row = smem_u32(stg) + lane * 64;
-      const int row0 = mb * BM + q * 32;
+      const int row0 = trow0 + q * 32;
       auto store32 = [&](const float* v, int col) {
         if (lane == 0) tma_store_wait_read<0>();   // the previous chunk's store has finished reading the buffer
         __syncwarp();
@@ -341,7 +382,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if constexpr (CTAS == 2) mbar_arrive_remote(tempty_leader + uint32_t(as) * 8u);
+      else mbar_arrive(&tempty_bar[as]);
       if (warp == 4) GEMM_TRACE(7, ti);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -349,31 +391,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // neither CTA's barriers / TMEM go away while the peer still signals them
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (CTAS == 2) tmem_dealloc_pair<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W, int ldw, cudaStream_t stream) {
+  using L = GemmSmem<BN, CTAS>;
   CUtensorMap ta, tb;
   int rc = a.a_kblock ? bya_host::encode_tmap_bf16(&ta, A, a.a_kblock, a.M, uint64_t(lda) * 2, BK, BM, a.K / a.a_kblock,
                                                    uint64_t(a.a_kblock_stride) * 2)
                       : bya_host::encode_tmap_bf16(&ta, A, a.K, a.M, uint64_t(lda) * 2, BK, BM);
   if (rc) return rc;
-  rc = bya_host::encode_tmap_bf16(&tb, W, a.K, a.N, uint64_t(ldw) * 2, BK, BN);
+  rc = bya_host::encode_tmap_bf16(&tb, W, a.K, a.N, uint64_t(ldw) * 2, BK, L::kBRows);
   if (rc) return rc;
   CUtensorMap tc;   // output: 32 x 32 boxes; with col_block a 3-D [dest][row][col] view of the send buffer
   rc = a.col_block ? bya_host::encode_tmap_bf16(&tc, a.out, a.col_block, a.M, uint64_t(a.ldc) * 2, 32, 32, a.N / a.col_block,
                                                 uint64_t(a.col_block_stride) * 2)
                    : bya_host::encode_tmap_bf16(&tc, a.out, a.N, a.M, uint64_t(a.ldc) * 2, 32, 32);
   if (rc) return rc;
-  auto kern = gemm_bf16_kernel<BN>;
+  auto kern = gemm_bf16_kernel<BN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess)
       return BYA_ERR_CUDA;
     attr_set = true;
   }
@@ -385,10 +430,45 @@ static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W,
       cudaMemcpyToSymbol(g_gemm_trace, &ptr, sizeof(ptr));
     }
   }
-  const int num_tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
-  const int grid = num_tiles < bya_host::num_sms() ? num_tiles : bya_host::num_sms();
-  kern<<<grid, kThreads, GemmSmem<BN>::kTotal, stream>>>(ta, tb, tc, a);
+  const int num_tiles = ((a.M + BM * CTAS - 1) / (BM * CTAS)) * (a.N / BN);
+  if constexpr (CTAS == 1) {
+    const int grid = num_tiles < bya_host::num_sms() ? num_tiles : bya_host::num_sms();
+    kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, tc, a);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // CTA pairs that can be resident at once (a persistent grid must not exceed it): one per TPC
+    static int max_pairs = 0;
+    if (!max_pairs) {
+      cfg.gridDim = dim3(bya_host::num_sms());
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = bya_host::num_sms() / 2;
+      max_pairs = n;
+    }
+    const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+    cfg.gridDim = dim3(2 * pairs);
+    if (cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, a) != cudaSuccess) return BYA_ERR_CUDA;
+  }
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
+}
+
+// CTA-pair policy: BYA_GEMM_CTAS=1 / 2 forces a build (A/B timing); default: pairs whenever the shape allows it
+static int gemm_ctas_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("BYA_GEMM_CTAS");
+    v = e ? std::atoi(e) : 0;
+  }
+  return v;
 }
 
 }  // namespace bya
@@ -413,8 +493,14 @@ extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W
   if (a.col_block == a.N) a.col_block = 0;   // a single column block is the plain layout
   if (a.a_kblock && (a.a_kblock % BK || a.K % a.a_kblock || a.a_kblock_stride % 8)) return BYA_ERR_SHAPE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a.N % 256 == 0) return launch_gemm<256>(a, A, lda, W, ldw, s);
-  if (a.N % 128 == 0) return launch_gemm<128>(a, A, lda, W, ldw, s);
-  if (a.N % 64 == 0) return launch_gemm<64>(a, A, lda, W, ldw, s);
+  const int force = gemm_ctas_override();
+  if (a.N % 256 == 0) {
+    // measured (gpurun_out/gemm_pair.log): pairs win 9-15 % on the K >= 3072 DiT shapes and lose 12 % on the K = 512
+    // router GEMMs, whose 8 k-blocks are over before the deeper pipeline and the cluster launch pay off
+    const bool pair = force ? force == 2 : (a.M > 256 && a.K >= 1024);
+    return pair ? launch_gemm<256, 2>(a, A, lda, W, ldw, s) : launch_gemm<256, 1>(a, A, lda, W, ldw, s);
+  }
+  if (a.N % 128 == 0) return launch_gemm<128, 1>(a, A, lda, W, ldw, s);
+  if (a.N % 64 == 0) return launch_gemm<64, 1>(a, A, lda, W, ldw, s);
   return BYA_ERR_SHAPE;
 }

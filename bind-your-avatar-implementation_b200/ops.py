@@ -1,5 +1,6 @@
-"""Thin Python wrappers over the C ABI (`include/bya.h`): tensor checks -> raw pointers -> libbya.so.
-torch is used only for device memory and the current stream."""
+"""Python-friendly signatures over the custom-op layer: tensor / shape checks here, then `torch.ops.bya.<name>`
+(`custom_ops.py`: one torch.library op per C-ABI entry point of `include/bya.h`, CUDA implementation only, raw pointers
++ the current stream into libbya.so).  torch is used only for device memory, streams and op dispatch."""
 from __future__ import annotations
 
 import ctypes
@@ -7,7 +8,10 @@ from typing import Optional
 
 import torch
 
-from .lib import ByaGemmArgs, check, lib
+from . import custom_ops  # noqa: F401  (defines torch.ops.bya.*)
+from .lib import check, lib
+
+_bya = torch.ops.bya
 
 EPI_STORE, EPI_RESIDUAL, EPI_QKV = 0, 1, 2
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
@@ -57,28 +61,18 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
         K = w.shape[1]
     if w.shape[1] != K or out.shape[0] != M or (out.shape[1] != (col_block if col_block else N)):
         raise RuntimeError(f"bya_b200.gemm: shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
-    args = ByaGemmArgs()
-    args.M, args.N, args.K = M, N, K
-    args.mode, args.act, args.group_m = mode, act, group_m
-    args.bias = _ptr(bias)
-    args.out, args.ldc = _ptr(out), out.stride(0)
+    rope_cos = rope_sin = None
+    nq_w = nq_b = nk_w = nk_b = None
     if mode == EPI_RESIDUAL:
         _bf16_2d(resid, "resid")
-        args.resid, args.ldr = _ptr(resid), resid.stride(0)
-        args.gate_a, args.gate_b = _ptr(gate_a), _ptr(gate_b)
-        args.row_bias_scale = _ptr(row_bias_scale)
-    args.split_row = split_row
-    args.alpha = alpha
+    else:
+        resid = gate_a = gate_b = row_bias_scale = None
     if mode == EPI_QKV:
-        cos, sin = rope
-        args.qkv_block, args.ln_eps = qkv_block, ln_eps
-        args.rope_cos, args.rope_sin, args.rope_row0 = _ptr(cos), _ptr(sin), rope_row0
-        args.nq_w, args.nq_b, args.nk_w, args.nk_b = _ptr(nq[0]), _ptr(nq[1]), _ptr(nk[0]), _ptr(nk[1])
-    args.col_block, args.col_block_stride = col_block, col_block_stride
-    args.a_kblock, args.a_kblock_stride = a_kblock, a_kblock_stride
-    args.q_premul = q_premul
-    rc = lib().bya_gemm_bf16(_stream(), _ptr(a), a.stride(0), _ptr(w), w.stride(0), ctypes.byref(args))
-    check(rc, "gemm")
+        rope_cos, rope_sin = rope
+        (nq_w, nq_b), (nk_w, nk_b) = nq, nk
+    _bya.gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, float(alpha), row_bias_scale, qkv_block,
+                   float(ln_eps), rope_cos, rope_sin, rope_row0, nq_w, nq_b, nk_w, nk_b, group_m, col_block, col_block_stride,
+                   a_kblock, a_kblock_stride, float(q_premul))
     LAUNCHES += 1
     return out
 
@@ -98,18 +92,11 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.
     if not (q.stride(0) == k.stride(0) == v.stride(0)):
         raise RuntimeError("bya_b200.attention_d64: q, k, v must share a row stride")
     ev = _prof(tag)
-    if score_bound_log2 is not None:
-        rc = lib().bya_attention_d64_bounded(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
-                                             batch, seq, heads, ctypes.c_float(score_bound_log2))
-    elif seq_stride is not None:
-        rc = lib().bya_attention_d64_strided(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
-                                             batch, seq, seq_stride, heads, ctypes.c_float(scale))
-    else:
-        rc = lib().bya_attention_d64(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0),
-                                     batch, seq, heads, ctypes.c_float(scale))
+    variant = 2 if score_bound_log2 is not None else (1 if seq_stride is not None else 0)
+    _bya.attention_d64(q, k, v, out, batch, seq, stride, heads, float(scale),
+                       float(score_bound_log2) if score_bound_log2 is not None else 0.0, variant)
     if ev is not None:
         ev.record()
-    check(rc, "attention_d64")
     LAUNCHES += 1
     return out
 
@@ -134,16 +121,11 @@ def layernorm_modulate(x, out, *, eps=1e-5, gamma=None, beta=None, mod_a=None, m
     sb, hb = (mod_b if mod_b is not None else (None, None))
     for t in (sa, ha, sb, hb):
         _f32(t, "modulation")
-    add_rows = 0
     if add is not None:
         _bf16_2d(add, "add")
         if not add.is_contiguous() or add.shape[1] != dim:
             raise RuntimeError("bya_b200.layernorm_modulate: add must be contiguous [rows, dim]")
-        add_rows = add.shape[0]
-    rc = lib().bya_layernorm_modulate(_stream(), _ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, dim,
-                                      ctypes.c_float(eps), _ptr(gamma), _ptr(beta), _ptr(sa), _ptr(ha), _ptr(sb),
-                                      _ptr(hb), split_row, _ptr(add), add_rows)
-    check(rc, "layernorm_modulate")
+    _bya.layernorm_modulate(x, out, float(eps), gamma, beta, sa, ha, sb, hb, split_row, add)
     _count()
     return out
 
@@ -157,7 +139,7 @@ def gemv(w, bias, x, y, in_act=0, out_act=0):
     N = w.shape[0]
     if w.shape[1] != K or tuple(y.shape) != (B, N):
         raise RuntimeError("bya_b200.gemv: shape mismatch")
-    check(lib().bya_gemv(_stream(), _ptr(w), _ptr(bias), _ptr(x), _ptr(y), B, N, K, in_act, out_act), "gemv")
+    _bya.gemv(w, bias, x, y, in_act, out_act)
     _count()
     return y
 
@@ -166,7 +148,7 @@ def timestep_features(t, out):
     if t.dtype != torch.int64 or not t.is_cuda:
         raise RuntimeError("bya_b200.timestep_features: timestep must be CUDA int64")
     _f32(out, "out")
-    check(lib().bya_timestep_features(_stream(), _ptr(t), _ptr(out), out.shape[0], out.shape[1]), "timestep_features")
+    _bya.timestep_features(t, out)
     _count()
     return out
 
@@ -177,7 +159,7 @@ def patchify(latents, out):
     if latents.dtype != torch.bfloat16 or not latents.is_contiguous():
         raise RuntimeError("bya_b200.patchify: latents must be contiguous bf16")
     _bf16_2d(out, "out")
-    check(lib().bya_patchify(_stream(), _ptr(latents), _ptr(out), F, C, H, W, out.stride(0)), "patchify")
+    _bya.patchify(latents, out)
     _count()
     return out
 
@@ -188,14 +170,14 @@ def unpatchify(y, out):
     _bf16_2d(y, "y")
     if out.dtype != torch.bfloat16 or not out.is_contiguous():
         raise RuntimeError("bya_b200.unpatchify: out must be contiguous bf16")
-    check(lib().bya_unpatchify(_stream(), _ptr(y), y.stride(0), _ptr(out), F, C, H // 2, W // 2), "unpatchify")
+    _bya.unpatchify(y, out)
     _count()
     return out
 
 
 def router_head(x, w, b, r, rows, chars):
     _bf16_2d(x, "x"), _f32(r, "r")
-    check(lib().bya_router_head(_stream(), _ptr(x), _ptr(w), _ptr(b), _ptr(r), rows, chars, x.shape[1]), "router_head")
+    _bya.router_head(x, w, b, r, rows, chars)
     _count()
     return r
 
@@ -211,20 +193,14 @@ def xattn_kv32(q, K, Vt, w, out, heads, head_dim, chars, kv_frames, scale, tok_b
         raise RuntimeError("bya_b200.xattn_kv32: K / Vt must be contiguous bf16")
     if w is not None and tuple(w.shape) != (tokens, chars):
         raise RuntimeError("bya_b200.xattn_kv32: w must be [tokens, chars]")
-    rc = lib().bya_xattn_kv32(_stream(), _ptr(q), q.stride(0), _ptr(K), _ptr(Vt), _ptr(w), _ptr(out), out.stride(0),
-                              tokens, heads, head_dim, chars, kv_frames, ctypes.c_float(scale),
-                              ctypes.c_longlong(tok_begin), ctypes.c_longlong(total_tokens))
-    check(rc, "xattn_kv32")
+    _bya.xattn_kv32(q, K, Vt, w, out, heads, head_dim, chars, kv_frames, float(scale), int(tok_begin), int(total_tokens))
     _count()
     return out
 
 
 def small_attention(qkv, out, n_seq, seq_len, heads, inner, outer_stride, tok_stride, scale=0.125):
     _bf16_2d(qkv, "qkv"), _bf16_2d(out, "out")
-    rc = lib().bya_small_attention(_stream(), _ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), n_seq, seq_len, heads,
-                                   inner, ctypes.c_longlong(outer_stride), ctypes.c_longlong(tok_stride),
-                                   ctypes.c_float(scale))
-    check(rc, "small_attention")
+    _bya.small_attention(qkv, out, n_seq, seq_len, heads, inner, int(outer_stride), int(tok_stride), float(scale))
     _count()
     return out
 
@@ -239,9 +215,7 @@ def masks_to_routing(masks, frames, grid_h, grid_w, index_mask=None, logits=None
         index_mask = torch.empty(n, dtype=torch.int64, device=masks.device)
     if logits is None:
         logits = torch.empty(n, C, dtype=torch.float32, device=masks.device)
-    rc = lib().bya_masks_to_routing(_stream(), _ptr(masks), C, T, H, W, frames, grid_h, grid_w, _ptr(index_mask),
-                                    _ptr(logits))
-    check(rc, "masks_to_routing")
+    _bya.masks_to_routing(masks, frames, grid_h, grid_w, index_mask, logits)
     _count()
     return index_mask, logits
 
@@ -249,7 +223,7 @@ def masks_to_routing(masks, frames, grid_h, grid_w, index_mask=None, logits=None
 def routing_frame_or(logits, out, frames):
     _f32(logits, "logits"), _f32(out, "out")
     n, C = logits.shape
-    check(lib().bya_routing_frame_or(_stream(), _ptr(logits), _ptr(out), frames, n // frames, C), "routing_frame_or")
+    _bya.routing_frame_or(logits, out, frames)
     _count()
     return out
 
@@ -257,7 +231,7 @@ def routing_frame_or(logits, out, frames):
 def audio_weights(af, routing, w, wsum=None):
     _f32(af, "af"), _f32(routing, "routing"), _f32(w, "w"), _f32(wsum, "wsum")
     n, C = routing.shape
-    check(lib().bya_audio_weights(_stream(), _ptr(af), _ptr(routing), _ptr(w), _ptr(wsum), n, C), "audio_weights")
+    _bya.audio_weights(af, routing, w, wsum)
     _count()
     return w
 
@@ -273,8 +247,6 @@ def cfg_dpm_step(model_out, sample, prev_sample, old_pred, pred_out, noise, coef
     sample / prev_sample: bf16 [.., F, C, H, W] (may alias); old_pred / pred_out: fp32 same numel (may alias);
     noise: bf16 [steps, 2, numel]; coef: fp32 [steps, DPM_NCOEF]; step_index: int32 [1] on the device or None;
     model_input: optional bf16 [Bin, F, Cin, H, W] whose channels [0, C) receive x_{t-1}."""
-    from .lib import ByaDpmStepArgs
-
     F, C, H, W = sample.shape[-4:]
     n = F * C * H * W
 
@@ -289,22 +261,15 @@ def cfg_dpm_step(model_out, sample, prev_sample, old_pred, pred_out, noise, coef
     if noise.dim() != 3 or noise.shape[1] != 2 or noise.shape[2] != n or coef.dim() != 2 or coef.shape[1] != DPM_NCOEF \
             or coef.shape[0] != noise.shape[0]:
         raise RuntimeError("bya_b200.cfg_dpm_step: noise must be [steps, 2, numel] and coef [steps, 12]")
-    a = ByaDpmStepArgs()
-    a.frames, a.channels, a.hw, a.prediction_type = F, C, H * W, prediction_type
     if model_out.dtype == torch.float32:
         chk(model_out, "model_out", torch.float32, n)
-        a.cfg_batch, a.model_out, a.model_out_f32 = 1, None, model_out.data_ptr()
     else:
         chk(model_out, "model_out", torch.bfloat16)
         if model_out.numel() not in (n, 2 * n):
             raise RuntimeError("bya_b200.cfg_dpm_step: model_out must hold one or two (CFG) predictions")
-        a.cfg_batch, a.model_out, a.model_out_f32 = model_out.numel() // n, model_out.data_ptr(), None
-    a.sample, a.prev_sample = sample.data_ptr(), prev_sample.data_ptr()
-    a.old_pred, a.pred_out, a.noise, a.coef = old_pred.data_ptr(), pred_out.data_ptr(), noise.data_ptr(), coef.data_ptr()
     if step_index is not None:
         if step_index.dtype != torch.int32 or not step_index.is_cuda:
             raise RuntimeError("bya_b200.cfg_dpm_step: step_index must be a CUDA int32 tensor")
-        a.step_index = step_index.data_ptr()
     elif coef.shape[0] != 1:
         raise RuntimeError("bya_b200.cfg_dpm_step: without step_index pass exactly this step's coef row and noise pair")
     if model_input is not None:
@@ -312,8 +277,7 @@ def cfg_dpm_step(model_out, sample, prev_sample, old_pred, pred_out, noise, coef
         Bi, Fi, Ci, Hi, Wi = model_input.shape
         if (Fi, Hi, Wi) != (F, H, W) or Ci < C:
             raise RuntimeError("bya_b200.cfg_dpm_step: model_input must be [B, F, >=C, H, W]")
-        a.model_input, a.in_batch, a.in_channels = model_input.data_ptr(), Bi, Ci
-    check(lib().bya_cfg_dpm_step(_stream(), ctypes.byref(a)), "cfg_dpm_step")
+    _bya.cfg_dpm_step(model_out, sample, prev_sample, old_pred, pred_out, noise, coef, prediction_type, step_index, model_input)
     _count()
     return prev_sample, pred_out
 
@@ -324,7 +288,6 @@ def denoise_select_step(timesteps, timestep_out, counter, step_index):
             or step_index.dtype != torch.int32 or not (timesteps.is_cuda and timestep_out.is_cuda and counter.is_cuda
                                                        and step_index.is_cuda):
         raise RuntimeError("bya_b200.denoise_select_step: int64 timestep tensors and int32 counters on the device")
-    check(lib().bya_denoise_select_step(_stream(), _ptr(timesteps), timesteps.numel(), _ptr(timestep_out),
-                                        timestep_out.numel(), _ptr(counter), _ptr(step_index)), "denoise_select_step")
+    _bya.denoise_select_step(timesteps, timestep_out, counter, step_index)
     _count()
     return timestep_out

@@ -86,8 +86,11 @@ def depth_parity(cfg, forced_masks=False, seed=1234, zero_uncond_audio=True, log
         if not want_tap(k) or k not in ours:
             return
         ref = v.detach().float()
+        a = ours.pop(k).float()
+        if ref.numel() != a.numel():      # the product taps batch element 0 only
+            ref = ref[0]
         scale = float(ref.abs().max()) + 1e-30
-        a = ours.pop(k).float().reshape(ref.shape)
+        a = a.reshape(ref.shape)
         r = {"cos": _cos(a, ref), "rel_max": float((a - ref).abs().max()) / scale}
         if k in bf:
             b = bf.pop(k).float().reshape(ref.shape)

@@ -96,6 +96,29 @@ def test_no_cpu_fallback():
         ops.layernorm_modulate(torch.zeros(4, 512, dtype=torch.bfloat16), torch.zeros(4, 512, dtype=torch.bfloat16))
 
 
+def test_every_c_abi_compute_entry_point_is_a_torch_custom_op():
+    """BASELINE.json north_star: "thin C-ABI torch custom-op layer".  Every compute entry point `include/bya.h` declares
+    is registered as `torch.ops.bya.<name>` with a CUDA kernel ONLY (no CPU / composite registration = no fallback), and
+    the dispatcher refuses CPU tensors."""
+    import re
+
+    import bya_b200  # noqa: F401
+    from bya_b200 import custom_ops
+
+    hdr = open(os.path.join(ROOT, "include", "bya.h")).read()
+    declared = set(re.findall(r"^int (bya_[a-z0-9_]+)\(", hdr, re.M)) - {"bya_abi_version", "bya_check_device"}
+    covered = {"bya_" + n for n in custom_ops.OP_NAMES} | {"bya_attention_d64_strided", "bya_attention_d64_bounded"}
+    assert declared <= covered, sorted(declared - covered)
+    for n in custom_ops.OP_NAMES:
+        op = getattr(torch.ops.bya, n).default
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(op.name(), "CUDA"), n
+        for key in ("CPU", "CompositeImplicitAutograd", "CompositeExplicitAutograd", "Meta"):
+            assert not torch._C._dispatch_has_kernel_for_dispatch_key(op.name(), key), (n, key)
+    z = torch.zeros(4, 512, dtype=torch.bfloat16)
+    with pytest.raises(NotImplementedError):
+        torch.ops.bya.layernorm_modulate(z, z.clone(), 1e-5, None, None, None, None, None, None, 0, None)
+
+
 def test_product_package_never_imports_oracle():
     pkg = os.path.join(ROOT, "bind-your-avatar-implementation_b200")
     for dirpath, _, files in os.walk(pkg):

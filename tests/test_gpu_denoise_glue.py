@@ -34,7 +34,7 @@ def test_cfg_dpm_step_kernel_bit_exact(built, prediction_type, cfg_batch):
     n = F * C * H * W
     # epsilon prediction divides by sqrt(alpha_t): keep alpha_999 > 0 for it (CogVideoX itself is v_prediction)
     kw = dict(prediction_type=prediction_type, rescale_betas_zero_snr=prediction_type != "epsilon")
-    sch, orc = CogVideoXDPMScheduler(**kw), DPMSchedulerOracle(**kw)
+    sch, orc = CogVideoXDPMScheduler.cogvideox_5b(**kw), DPMSchedulerOracle(**kw)
     sch.set_timesteps(5)   # 999, 799, ..., 199: the last step lands on alpha = 1 (first order, no noise)
     orc.set_timesteps(5)
     ts = sch.timesteps.tolist()

@@ -46,7 +46,7 @@ def _check(res, min_cos, max_rel):
 def test_c2_full_depth_soft_router_vs_fp32_oracle(built):
     """configs[1]: 42 layers, 49 frames 480x720, 2 characters, B=1, learned soft router, face + audio cross-attention."""
     from bya_b200.synth import CONFIGS
-    from tests.depth_parity import depth_parity
+    from depth_parity import depth_parity
 
     res = depth_parity(CONFIGS["c2"])
     _dump("depth_parity_c2_soft.json", res)
@@ -59,7 +59,7 @@ def test_c3_full_depth_forced_masks_cfg_batch2(built):
     """configs[2] geometry: CFG batch 2 (unconditional branch with zeroed audio), stage-2 forced hard masks (router
     skipped, frame-OR, bit-exact audio weights), 42 layers at the full grid."""
     from bya_b200.synth import CONFIGS
-    from tests.depth_parity import depth_parity
+    from depth_parity import depth_parity
 
     res = depth_parity(CONFIGS["c3"], forced_masks=True)
     _dump("depth_parity_c3_forced.json", res)

@@ -14,7 +14,8 @@ def main():
 
     g.build()
     from bya_b200.synth import CONFIGS
-    from tests.depth_parity import depth_parity, format_report
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from depth_parity import depth_parity, format_report
 
     name = next((a for a in sys.argv[1:] if a in CONFIGS), "c2")
     forced = "forced" in sys.argv[1:]
