@@ -93,7 +93,8 @@ def depth_parity(cfg, forced_masks=False, seed=1234, zero_uncond_audio=True, log
         a = a.reshape(ref.shape)
         r = {"cos": _cos(a, ref), "rel_max": float((a - ref).abs().max()) / scale}
         if k in bf:
-            b = bf.pop(k).float().reshape(ref.shape)
+            b = bf.pop(k).float()
+            b = (b[0] if b.numel() != ref.numel() else b).reshape(ref.shape)
             r["cos_bf16"], r["rel_max_bf16"] = _cos(b, ref), float((b - ref).abs().max()) / scale
         rows[k] = r
 
