@@ -23,7 +23,7 @@ class ByaGemmArgs(ctypes.Structure):
         ("nq_w", ctypes.c_void_p), ("nq_b", ctypes.c_void_p), ("nk_w", ctypes.c_void_p), ("nk_b", ctypes.c_void_p),
         ("col_block", ctypes.c_int), ("col_block_stride", ctypes.c_longlong),
         ("a_kblock", ctypes.c_int), ("a_kblock_stride", ctypes.c_longlong),
-        ("q_premul", ctypes.c_float),
+        ("q_premul", ctypes.c_float), ("split_k", ctypes.c_int),
     ]
 
 

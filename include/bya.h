@@ -31,8 +31,10 @@ int bya_check_device(void);
 /* ---------------------------------------------------------------- GEMM  out = epilogue(A[M,K] · W[N,K]^T)
  * Replaces every nn.Linear on the path: transformer.py:200-221 (attn1 / ff), router.py:226-228, :301-302, :430-466,
  * audio_model.py:179-185, plus the elementwise ops that follow them in the reference (see epilogue modes). */
-enum { GEMM_EPI_STORE = 0, GEMM_EPI_RESIDUAL = 1, GEMM_EPI_QKV = 2 };
-enum { GEMM_ACT_NONE = 0, GEMM_ACT_GELU_TANH = 1, GEMM_ACT_GELU_ERF = 2 };
+enum { GEMM_EPI_STORE = 0, GEMM_EPI_RESIDUAL = 1, GEMM_EPI_QKV = 2,
+       GEMM_EPI_SPLITK_F32 = 3 /* out is an fp32 [M, ldc] workspace (zero before the call): every k-split ADDS its partial
+                                  product with red.global.add.f32; bias / act are applied by bya_splitk_finalize */ };
+enum { GEMM_ACT_NONE = 0, GEMM_ACT_GELU_TANH = 1, GEMM_ACT_GELU_ERF = 2, GEMM_ACT_RELU = 3 };
 
 typedef struct ByaGemmArgs {
   int M, N, K;            /* K % 64 == 0, N % 64 == 0 */
@@ -74,6 +76,10 @@ typedef struct ByaGemmArgs {
    * q_premul = head_dim^-1/2 * log2(e) the scores Q K^T come out in log2 units, which is what
    * bya_attention_d64_bounded consumes (the softmax scale of diffusers' Attention folded into the projection). */
   float q_premul;
+  /* GEMM_EPI_SPLITK_F32 only: the K range is cut into split_k parts that run as independent tiles (skinny,
+   * weight-streaming GEMMs of the per-generation prologue — audio_model.py:78-114: M <= 128 rows against a 2.4 GB
+   * weight — need more than N / 256 CTAs to pull HBM bandwidth).  0 / 1 -> off. */
+  int split_k;
 } ByaGemmArgs;
 
 int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W, int ldw, const ByaGemmArgs* args);
@@ -151,6 +157,33 @@ int bya_routing_frame_or(void* stream, const float* logits, float* out, int fram
 /* w[n,c] = 1 - max_{c'!=c} (af @ r[n])[c'] (== 1 - swap(af@r) for two characters), wsum[n] = sum_c w[n,c] (may be
  * NULL): transformer.py:860-863,:899-900 */
 int bya_audio_weights(void* stream, const float* af, const float* routing, float* w, float* wsum, int tokens, int chars);
+
+/* ---------------------------------------------------------------- per-generation prologue helpers
+ * The timestep-invariant sub-graphs (LocalFacialExtractor router.py:157-193, AudioProjModel audio_model.py:78-114, face /
+ * router / audio K-V precompute router.py:247-254,:377-383, audio_model.py:241-256) run on bya_gemm_bf16,
+ * bya_layernorm_*, bya_attention_d64 plus the data-movement kernels below; nothing of it goes through a library. */
+
+/* out[r, c] = (bf16) src[r, c] for r < rows, c < cols; src is bf16 (src_f32 == 0) or fp32; row strides in elements.
+ * torch.cat / repeat / unfold / .to(bf16) of the reference's prologue (router.py:166-176, audio_model.py:188-193). */
+int bya_copy2d(void* stream, const void* src, long long lds, int src_f32, void* out, long long ldo, int rows, int cols);
+/* Zero `bytes` bytes (a memset node, no kernel): split-K workspaces, padded operand tails. */
+int bya_memset_zero(void* stream, void* ptr, long long bytes);
+/* out[r, c] = act(ws[r, c] + bias[c]) as bf16, then ws[r, c] = 0 (ready for the next split-K GEMM). act: GEMM_ACT_* */
+int bya_splitk_finalize(void* stream, float* ws, long long ldw, const void* bias, int act, void* out, long long ldo, int rows,
+                        int cols);
+/* LayerNorm(dim 1024, affine) followed by LeakyReLU(0.01): the `Linear -> LayerNorm -> LeakyReLU` stages of
+ * LocalFacialExtractor's mapping MLPs (router.py:118-154). */
+int bya_layernorm_leakyrelu(void* stream, const void* x, int ldx, void* out, int ldo, int rows, int dim, float eps,
+                            const void* gamma, const void* beta, float slope);
+/* x [groups*32, ldx]: k of head h at columns k_off + h*head_dim.., v at v_off + h*head_dim..  ->  K [groups][heads][32]
+ * [head_dim], Vt [groups][heads][head_dim][32]: the layouts bya_xattn_kv32 consumes (the reference's reshape_tensor /
+ * transpose of router.py:250-254 and diffusers' head split of audio_model.py:179-185). */
+int bya_kv_pack(void* stream, const void* x, long long ldx, int k_off, int v_off, void* K, void* Vt, int groups, int heads,
+                int head_dim);
+/* k [chars*32, ldk] (routed keys, natural head-major columns h*head_dim + d) -> block-structured score matrix
+ * [chars*32*heads, heads*head_dim]: row (c, tok*heads + h) holds the key of head h in columns h*head_dim.., zeros
+ * elsewhere — so that the router's per-head q.k^T (router.py:385-393) is one dense GEMM against it. */
+int bya_router_keys_scatter(void* stream, const void* k, long long ldk, void* mat, int chars, int heads, int head_dim);
 
 /* ---------------------------------------------------------------- the step either side of the path
  * Classifier-free-guidance combine + CogVideoXDPMScheduler.step + the write of x_{t-1} into the next step's model
