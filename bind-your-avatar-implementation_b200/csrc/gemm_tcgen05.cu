@@ -79,7 +79,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_m = (p.M + TM - 1) / TM;
   const int num_n = p.N / BN;
-  const int num_tiles = num_m * num_n;
+  const int splits = p.split_k > 1 ? p.split_k : 1;   // GEMM_EPI_SPLITK_F32: k-ranges run as independent tiles
+  const int num_tiles = num_m * num_n * splits;
   const int num_kb = p.K / BK;
   constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
 
@@ -111,7 +112,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   // tile -> (m_blk, n_blk): groups of `group_m` row-blocks sweep all column-blocks, so that concurrently running
   // CTAs share a small set of A and W tiles in L2.
+  auto k_range = [&](int t, int& kb0, int& kb1) {
+    const int ks = t % splits;
+    kb0 = int((long long)ks * num_kb / splits);
+    kb1 = int((long long)(ks + 1) * num_kb / splits);
+  };
   auto tile_coord = [&](int t, int& mb, int& nb) {
+    t /= splits;
     const int gm = p.group_m;
     const int per_group = gm * num_n;
     const int g = t / per_group;
@@ -133,10 +140,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tile_coord(t, mb, nb);
         const int arow = mb * TM + int(rank) * BM;             // this CTA's 128 rows of A
         const int brow = nb * BN + int(rank) * L::kBRows;      // this CTA's share of the weight rows
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0, kb1;
+        k_range(t, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (kb == 0) GEMM_TRACE(0, ti);
-          if (kb == num_kb - 1) GEMM_TRACE(1, ti);
+          if (kb == kb0) GEMM_TRACE(0, ti);
+          if (kb == kb1 - 1) GEMM_TRACE(1, ti);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           if constexpr (CTAS == 2) {
@@ -177,10 +186,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       GEMM_TRACE(2, ti);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      int kb0, kb1;
+      k_range(t, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
-        if (kb == 0) GEMM_TRACE(3, ti);
-        if (kb == num_kb - 1) GEMM_TRACE(4, ti);
+        if (kb == kb0) GEMM_TRACE(3, ti);
+        if (kb == kb1 - 1) GEMM_TRACE(4, ti);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
@@ -189,15 +200,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t db = make_smem_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            if constexpr (CTAS == 2) umma_ss_pair(tmem_acc, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0);
-            else umma_ss(tmem_acc, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            if constexpr (CTAS == 2) umma_ss_pair(tmem_acc, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, acc);
+            else umma_ss(tmem_acc, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, acc);
           }
           if constexpr (CTAS == 2) {   // both CTAs' producers / epilogues are released by the same completion
             umma_commit_pair(&empty_bar[stage]);
-            if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[as]);
+            if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[as]);
           } else {
             umma_commit(&empty_bar[stage]);
-            if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
           }
         }
         __syncwarp();
@@ -264,7 +276,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       };
 
-      if (p.mode == GEMM_EPI_QKV) {
+      if (p.mode == GEMM_EPI_SPLITK_F32) {
+        // partial product of one k-range -> its own fp32 slice [ks][M][ldc] of the workspace (plain stores: the
+        // reduction over the slices, bias and activation happen in bya_splitk_finalize in a FIXED order, so the
+        // result does not depend on which CTA finished first)
+        float* orow = reinterpret_cast<float*>(p.out) + (size_t(t % splits) * p.M + size_t(row_ok ? row : 0)) * p.ldc + col0;
+        constexpr int CH = (BN >= 64) ? 32 : BN / 2;
+        constexpr int NCH = (BN / 2) / CH;
+#pragma unroll 1
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = half * (BN / 2) + ci * CH;
+          uint32_t r[CH];
+          if (CH == 32) tmem_ld_x32(taddr + c, r);
+          else tmem_ld_x16(taddr + c, r);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 4)
+              *reinterpret_cast<float4*>(orow + c + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                     __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          }
+        }
+      } else if (p.mode == GEMM_EPI_QKV) {
         // one 64-wide head per iteration: + bias, LayerNorm(64) on q/k heads, RoPE on video rows
         const bool is_video = row >= p.split_row;
         const float* cs = p.rope_cos + size_t(max(row - p.split_row, 0) + p.rope_row0) * 64;
@@ -365,6 +398,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else if (p.act == GEMM_ACT_GELU_ERF) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+          } else if (p.act == GEMM_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
           }
           if (resid_mode) {
 #pragma unroll
@@ -411,9 +447,11 @@ static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W,
   rc = bya_host::encode_tmap_bf16(&tb, W, a.K, a.N, uint64_t(ldw) * 2, BK, L::kBRows);
   if (rc) return rc;
   CUtensorMap tc;   // output: 32 x 32 boxes; with col_block a 3-D [dest][row][col] view of the send buffer
-  rc = a.col_block ? bya_host::encode_tmap_bf16(&tc, a.out, a.col_block, a.M, uint64_t(a.ldc) * 2, 32, 32, a.N / a.col_block,
-                                                uint64_t(a.col_block_stride) * 2)
-                   : bya_host::encode_tmap_bf16(&tc, a.out, a.N, a.M, uint64_t(a.ldc) * 2, 32, 32);
+  if (a.mode == GEMM_EPI_SPLITK_F32) tc = ta;   // fp32 workspace, written with plain vector stores: no store map
+  else
+    rc = a.col_block ? bya_host::encode_tmap_bf16(&tc, a.out, a.col_block, a.M, uint64_t(a.ldc) * 2, 32, 32, a.N / a.col_block,
+                                                  uint64_t(a.col_block_stride) * 2)
+                     : bya_host::encode_tmap_bf16(&tc, a.out, a.N, a.M, uint64_t(a.ldc) * 2, 32, 32);
   if (rc) return rc;
   auto kern = gemm_bf16_kernel<BN, CTAS>;
   static bool attr_set = false;
@@ -430,7 +468,7 @@ static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W,
       cudaMemcpyToSymbol(g_gemm_trace, &ptr, sizeof(ptr));
     }
   }
-  const int num_tiles = ((a.M + BM * CTAS - 1) / (BM * CTAS)) * (a.N / BN);
+  const int num_tiles = ((a.M + BM * CTAS - 1) / (BM * CTAS)) * (a.N / BN) * (a.split_k > 1 ? a.split_k : 1);
   if constexpr (CTAS == 1) {
     const int grid = num_tiles < bya_host::num_sms() ? num_tiles : bya_host::num_sms();
     kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, tc, a);
@@ -489,6 +527,13 @@ extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W
   }
   if (a.col_block && (a.col_block % 64 || a.N % a.col_block || a.col_block_stride % 8 || a.mode == GEMM_EPI_RESIDUAL))
     return BYA_ERR_SHAPE;
+  if (a.mode == GEMM_EPI_SPLITK_F32) {
+    if (a.col_block || a.ldc % 4 || (reinterpret_cast<uintptr_t>(a.out) & 15)) return BYA_ERR_SHAPE;
+    if (a.split_k < 1) a.split_k = 1;
+    if (a.split_k > a.K / BK) a.split_k = a.K / BK;
+  } else {
+    a.split_k = 0;
+  }
   if (a.a_kblock == a.K) a.a_kblock = 0;
   if (a.col_block == a.N) a.col_block = 0;   // a single column block is the plain layout
   if (a.a_kblock && (a.a_kblock % BK || a.K % a.a_kblock || a.a_kblock_stride % 8)) return BYA_ERR_SHAPE;
@@ -497,7 +542,7 @@ extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W
   if (a.N % 256 == 0) {
     // measured (gpurun_out/gemm_pair.log): pairs win 9-15 % on the K >= 3072 DiT shapes and lose 12 % on the K = 512
     // router GEMMs, whose 8 k-blocks are over before the deeper pipeline and the cluster launch pay off
-    const bool pair = force ? force == 2 : (a.M > 256 && a.K >= 1024);
+    const bool pair = a.mode != GEMM_EPI_SPLITK_F32 && (force ? force == 2 : (a.M > 256 && a.K >= 1024));
     return pair ? launch_gemm<256, 2>(a, A, lda, W, ldw, s) : launch_gemm<256, 1>(a, A, lda, W, ldw, s);
   }
   if (a.N % 128 == 0) return launch_gemm<128, 1>(a, A, lda, W, ldw, s);

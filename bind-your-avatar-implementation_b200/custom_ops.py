@@ -45,14 +45,14 @@ def _op(schema: str):
 @_op("gemm_bf16(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int act, int mode, Tensor? resid, Tensor? gate_a, "
      "Tensor? gate_b, int split_row, float alpha, Tensor? row_bias_scale, int qkv_block, float ln_eps, Tensor? rope_cos, "
      "Tensor? rope_sin, int rope_row0, Tensor? nq_w, Tensor? nq_b, Tensor? nk_w, Tensor? nk_b, int group_m, int col_block, "
-     "int col_block_stride, int a_kblock, int a_kblock_stride, float q_premul) -> ()")
+     "int col_block_stride, int a_kblock, int a_kblock_stride, float q_premul, int split_k) -> ()")
 def _gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, alpha, row_bias_scale, qkv_block, ln_eps,
                rope_cos, rope_sin, rope_row0, nq_w, nq_b, nk_w, nk_b, group_m, col_block, col_block_stride, a_kblock,
-               a_kblock_stride, q_premul):
+               a_kblock_stride, q_premul, split_k):
     g = ByaGemmArgs()
     g.M, g.N, g.K = a.shape[0], w.shape[0], w.shape[1]
     g.mode, g.act, g.group_m = mode, act, group_m
-    g.bias, g.out, g.ldc = _ptr(bias), _ptr(out), out.stride(0)
+    g.bias, g.out, g.ldc = _ptr(bias), _ptr(out), out.stride(-2)
     if resid is not None:
         g.resid, g.ldr = _ptr(resid), resid.stride(0)
     g.gate_a, g.gate_b, g.row_bias_scale = _ptr(gate_a), _ptr(gate_b), _ptr(row_bias_scale)
@@ -63,6 +63,7 @@ def _gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, alp
     g.col_block, g.col_block_stride = col_block, col_block_stride
     g.a_kblock, g.a_kblock_stride = a_kblock, a_kblock_stride
     g.q_premul = q_premul
+    g.split_k = split_k
     check(lib().bya_gemm_bf16(_stream(), _ptr(a), a.stride(0), _ptr(w), w.stride(0), ctypes.byref(g)), "gemm")
 
 
@@ -181,3 +182,43 @@ def _cfg_dpm_step(model_out, sample, prev_sample, old_pred, pred_out, noise, coe
 def _denoise_select_step(timesteps, timestep_out, counter, step_index):
     check(lib().bya_denoise_select_step(_stream(), _ptr(timesteps), timesteps.numel(), _ptr(timestep_out), timestep_out.numel(),
                                         _ptr(counter), _ptr(step_index)), "denoise_select_step")
+
+
+# ---------------------------------------------------------------- per-generation prologue helpers
+@_op("copy2d(Tensor src, Tensor(a!) out) -> ()")
+def _copy2d(src, out):
+    rows, cols = out.shape
+    check(lib().bya_copy2d(_stream(), _ptr(src), ctypes.c_longlong(src.stride(0)), int(src.dtype == torch.float32), _ptr(out),
+                           ctypes.c_longlong(out.stride(0)), rows, cols), "copy2d")
+
+
+@_op("memset_zero(Tensor(a!) t) -> ()")
+def _memset_zero(t):
+    check(lib().bya_memset_zero(_stream(), _ptr(t), ctypes.c_longlong(t.numel() * t.element_size())), "memset_zero")
+
+
+@_op("splitk_finalize(Tensor ws, int row0, Tensor? bias, int act, Tensor(a!) out) -> ()")
+def _splitk_finalize(ws, row0, bias, act, out):
+    rows, cols = out.shape
+    splits, ws_rows, _ = ws.shape
+    check(lib().bya_splitk_finalize(_stream(), _ptr(ws), splits, ws_rows, ctypes.c_longlong(ws.stride(1)), row0, _ptr(bias), act,
+                                    _ptr(out), ctypes.c_longlong(out.stride(0)), rows, cols), "splitk_finalize")
+
+
+@_op("layernorm_leakyrelu(Tensor x, Tensor(a!) out, float eps, Tensor gamma, Tensor beta, float slope) -> ()")
+def _layernorm_leakyrelu(x, out, eps, gamma, beta, slope):
+    rows, dim = x.shape
+    check(lib().bya_layernorm_leakyrelu(_stream(), _ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, dim, ctypes.c_float(eps),
+                                        _ptr(gamma), _ptr(beta), ctypes.c_float(slope)), "layernorm_leakyrelu")
+
+
+@_op("kv_pack(Tensor x, int k_off, int v_off, Tensor(a!) K, Tensor(b!) Vt) -> ()")
+def _kv_pack(x, k_off, v_off, K, Vt):
+    G, H, _, d = K.shape
+    check(lib().bya_kv_pack(_stream(), _ptr(x), ctypes.c_longlong(x.stride(0)), k_off, v_off, _ptr(K), _ptr(Vt), G, H, d), "kv_pack")
+
+
+@_op("router_keys_scatter(Tensor k, Tensor(a!) mat, int chars, int heads, int head_dim) -> ()")
+def _router_keys_scatter(k, mat, chars, heads, head_dim):
+    check(lib().bya_router_keys_scatter(_stream(), _ptr(k), ctypes.c_longlong(k.stride(0)), _ptr(mat), chars, heads, head_dim),
+          "router_keys_scatter")

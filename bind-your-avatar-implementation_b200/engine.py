@@ -79,6 +79,14 @@ class _Workspace:
             self.bufs[name] = t
         return t
 
+    def get_zeroed(self, name, shape, dtype=torch.bfloat16):
+        """Like get(), zero-filled (a memset node) when it is (re)allocated — split-K accumulators, which their
+        finalize kernel leaves clean, and operand regions that are never written."""
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = ops.memset_zero(self.get(name, shape, dtype))
+        return t
+
 
 def _tree_values(x):
     """Nested dict / list of tensors -> nested lists in a deterministic order."""
@@ -316,6 +324,9 @@ class StepEngine:
                 self.face.append(dict(ln=(_bf(ca.norm2.weight), _bf(ca.norm2.bias), ca.norm2.eps), w_q=_bf(ca.to_q.weight),
                                       w_o=_bf(ca.to_out.weight)))
             self.router = RouterPack(m.router)
+            from .prologue import ProloguePack
+
+            self.pro_pack = ProloguePack(m, router_feature_perm(m.router.heads, 2048 // m.router.heads, self.device))
         self.audio = []
         if getattr(m, "is_train_audio", False):
             for lyr in m.audio_model.layers:
@@ -326,42 +337,30 @@ class StepEngine:
 
     # ------------------------------------------------------------------------------------------------ prologue
     @torch.no_grad()
-    def prologue(self, id_cond, id_vit_hidden, audio_embeds, frames, use_router: bool):
-        """Timestep-invariant tensors of one generation; torch on the GPU, once per video."""
-        m = self.model
-        dt = torch.bfloat16
-        C = len(id_cond)
-        B = id_cond[0].shape[0]
-        out = dict(face_k=[], face_vt=[], kmat=[], aud_k=[], aud_vt=[])
-        face = torch.stack([m.local_facial_extractor(id_cond[c].to(self.device, dt),
-                                                     [v.to(self.device, dt) for v in id_vit_hidden[c]]) for c in range(C)], 1)
-        out["face_tokens"] = face  # [B,C,32,2048]
-        for b in range(B):
-            fk, fv, km = [], [], []
-            for j, ca in enumerate(m.perceiver_cross_attention):
-                k, v = ca.face_kv(face[b])
-                fk.append(k)
-                fv.append(v.transpose(-1, -2).contiguous())
-                km.append(m.router.router_keys(k, j) if use_router else None)
-            out["face_k"].append(fk)
-            out["face_vt"].append(fv)
-            out["kmat"].append(km)
-        if audio_embeds is not None and getattr(m, "is_train_audio", False):
-            a = audio_embeds.to(self.device, dt)
+    def prologue(self, id_cond, id_vit_hidden, audio_embeds, frames, use_router: bool, ws: Optional[_Workspace] = None):
+        """Timestep-invariant tensors of one generation on libbya.so kernels (`prologue.py`).
+        The results live in `ws` (named buffers): a holder that caches them (the eager per-generation cache, every
+        captured graph with its prologue outside the graph) passes a workspace of its own, so that recomputing for one
+        holder never rewrites what another one still reads."""
+        from . import prologue as pk
+
+        if not hasattr(self, "pro_pack"):
+            raise RuntimeError("bya_b200: the model was built without the face branch (is_train_face=False)")
+        P, dev = self.pro_pack, self.device
+        ws = ws if ws is not None else self.ws
+        C, B = len(id_cond), id_cond[0].shape[0]
+        face = pk.face_tokens(P, ws, id_cond, id_vit_hidden, dev)
+        out = pk.face_kv_and_router_keys(P, ws, face, use_router)
+        out["face_tokens"] = face                                  # [B,C,32,2048]
+        out["aud_k"], out["aud_vt"] = [], []
+        if audio_embeds is not None and P.audio is not None:
+            a = audio_embeds.to(dev, torch.bfloat16)
             if a.ndim != 5:
                 raise NotImplementedError("bya_b200: the single-speaker + mute-audio path (audio_embeds.ndim == 4) needs "
                                           "tests/input/ae_mute.pt, which the reference does not ship (audio_model.py:203)")
-            a = a.reshape(B * C, *a.shape[2:])
-            ctx = m.audio_model.proj_in(m.audio_model.sliding_windows(a, frames)).reshape(B, C, frames, 32, -1)
-            out["audio_ctx"] = ctx
-            for b in range(B):
-                ks, vs = [], []
-                for l in range(len(m.audio_model.layers)):
-                    k, vt = m.audio_model.audio_kv(ctx[b], l)
-                    ks.append(k)
-                    vs.append(vt)
-                out["aud_k"].append(ks)
-                out["aud_vt"].append(vs)
+            ctx = pk.audio_context(P, ws, a.reshape(B * C, *a.shape[2:]), frames)
+            out["audio_ctx"] = ctx.view(B, C, *ctx.shape[1:])
+            out["aud_k"], out["aud_vt"] = pk.audio_kv(P, ws, ctx, B, C)
         return out
 
     # ------------------------------------------------------------------------------------------------ sequence parallel
@@ -433,8 +432,10 @@ class StepEngine:
             rope = static["image_rotary_emb"]
             kw = dict(static, image_rotary_emb=None if rope is None else tuple(rope), per_frame_forcing=per_frame_forcing,
                       cache_prologue=False)
+            pro_ws = _Workspace(dev) if cache_prologue else None
             if cache_prologue:   # the prologue stays outside the graph: it is recomputed only when its inputs change
-                kw["_pro"] = self.prologue(static["id_cond"], static["id_vit_hidden"], static["audio_embeds"], Fr, use_router)
+                kw["_pro"] = self.prologue(static["id_cond"], static["id_vit_hidden"], static["audio_embeds"], Fr, use_router,
+                                           ws=pro_ws)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):      # warm-up outside capture: workspaces, tensor maps, lazy module state
@@ -446,17 +447,18 @@ class StepEngine:
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 out = self.step(**kw)
             g = dict(graph=graph, static=static, out=out, launches=ops.LAUNCHES - l0, pro=kw.get("_pro"), pro_key=key,
-                     pro_refs=self._prologue_refs_pending if cache_prologue else None)
+                     pro_refs=self._prologue_refs_pending if cache_prologue else None, pro_ws=pro_ws)
             self._graphs[sig] = g
         else:
             for dst, src in zip(flat(list(g["static"].values())), flat(list(nested.values()))):
                 if dst is not None:
                     dst.copy_(src, non_blocking=True)
             if cache_prologue and key != g["pro_key"]:
+                # same workspace, same shapes -> the results land in the buffers the captured graph reads
                 new = self.prologue(g["static"]["id_cond"], g["static"]["id_vit_hidden"], g["static"]["audio_embeds"], Fr,
-                                    use_router)
+                                    use_router, ws=g["pro_ws"])
                 for dst, src in zip(flat(_tree_values(g["pro"])), flat(_tree_values(new))):
-                    if dst is not None:
+                    if dst is not None and dst.data_ptr() != src.data_ptr():
                         dst.copy_(src)
                 g["pro_key"], g["pro_refs"] = key, self._prologue_refs_pending
         g["graph"].replay()
@@ -510,7 +512,10 @@ class StepEngine:
         else:
             key = self._prologue_cache_key(id_cond, id_vit_hidden, audio_embeds, Fr, use_router) if cache_prologue else None
             if key is None or key != self._prologue_key:
-                self._prologue = self.prologue(id_cond, id_vit_hidden, audio_embeds, Fr, use_router)
+                if cache_prologue and getattr(self, "_pro_ws", None) is None:
+                    self._pro_ws = _Workspace(dev)
+                self._prologue = self.prologue(id_cond, id_vit_hidden, audio_embeds, Fr, use_router,
+                                               ws=self._pro_ws if cache_prologue else None)
                 self._prologue_key = key
                 self._prologue_refs = self._prologue_refs_pending if cache_prologue else None
             pro = self._prologue

@@ -13,8 +13,8 @@ from .lib import check, lib
 
 _bya = torch.ops.bya
 
-EPI_STORE, EPI_RESIDUAL, EPI_QKV = 0, 1, 2
-ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
+EPI_STORE, EPI_RESIDUAL, EPI_QKV, EPI_SPLITK_F32 = 0, 1, 2, 3
+ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -49,17 +49,23 @@ def _bf16_2d(t: torch.Tensor, name: str):
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=ACT_NONE, mode=EPI_STORE,
          resid=None, gate_a=None, gate_b=None, split_row=0, alpha=1.0, row_bias_scale=None,
          qkv_block=0, ln_eps=1e-6, rope=None, rope_row0=0, nq=None, nk=None, group_m=0, col_block=0,
-         col_block_stride=0, a_kblock=0, a_kblock_stride=0, q_premul=0.0) -> torch.Tensor:
+         col_block_stride=0, a_kblock=0, a_kblock_stride=0, q_premul=0.0, split_k=0) -> torch.Tensor:
     """out = epilogue(a @ w.T); a [M,K], w [N,K], out [M,N] (row strides may exceed the width).
     With a_kblock: `a` is the first [M, a_kblock] block of K/a_kblock blocks a_kblock_stride elements apart.
     With col_block: `out` is the first [M, col_block] block of N/col_block blocks col_block_stride elements apart."""
     global LAUNCHES
-    _bf16_2d(a, "a"), _bf16_2d(w, "w"), _bf16_2d(out, "out")
+    _bf16_2d(a, "a"), _bf16_2d(w, "w")
     M, K = a.shape
     N = w.shape[0]
+    if mode == EPI_SPLITK_F32:
+        split_k = max(1, min(int(split_k), K // 64))
+        if out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous() or tuple(out.shape) != (split_k, M, N):
+            raise RuntimeError(f"bya_b200.gemm: the split-K workspace must be a contiguous CUDA fp32 [{split_k}, {M}, {N}] tensor")
+    else:
+        _bf16_2d(out, "out")
     if a_kblock:
         K = w.shape[1]
-    if w.shape[1] != K or out.shape[0] != M or (out.shape[1] != (col_block if col_block else N)):
+    if w.shape[1] != K or out.shape[-2] != M or (out.shape[-1] != (col_block if col_block else N)):
         raise RuntimeError(f"bya_b200.gemm: shape mismatch a{tuple(a.shape)} w{tuple(w.shape)} out{tuple(out.shape)}")
     rope_cos = rope_sin = None
     nq_w = nq_b = nk_w = nk_b = None
@@ -72,7 +78,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
         (nq_w, nq_b), (nk_w, nk_b) = nq, nk
     _bya.gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, float(alpha), row_bias_scale, qkv_block,
                    float(ln_eps), rope_cos, rope_sin, rope_row0, nq_w, nq_b, nk_w, nk_b, group_m, col_block, col_block_stride,
-                   a_kblock, a_kblock_stride, float(q_premul))
+                   a_kblock, a_kblock_stride, float(q_premul), split_k)
     LAUNCHES += 1
     return out
 
@@ -291,3 +297,61 @@ def denoise_select_step(timesteps, timestep_out, counter, step_index):
     _bya.denoise_select_step(timesteps, timestep_out, counter, step_index)
     _count()
     return timestep_out
+
+
+# ---------------------------------------------------------------- per-generation prologue helpers
+def copy2d(src, out):
+    """out[r, c] = bf16(src[r, c]); 2-D views with unit inner stride (src bf16 or fp32), row strides free."""
+    _bf16_2d(out, "out")
+    if src.dim() != 2 or src.stride(1) != 1 or not src.is_cuda or src.dtype not in (torch.bfloat16, torch.float32) \
+            or tuple(src.shape) != tuple(out.shape):
+        raise RuntimeError(f"bya_b200.copy2d: src {tuple(src.shape)} {src.dtype} vs out {tuple(out.shape)}")
+    _bya.copy2d(src, out)
+    _count()
+    return out
+
+
+def memset_zero(t):
+    if not t.is_cuda or not t.is_contiguous():
+        raise RuntimeError("bya_b200.memset_zero: contiguous CUDA tensor expected")
+    _bya.memset_zero(t)
+    return t
+
+
+def splitk_finalize(ws, bias, act, out, row0=0):
+    """out = act(sum_s ws[s, row0:row0+rows] + bias) as bf16; ws fp32 [splits, M, N] filled by gemm(mode=EPI_SPLITK_F32)."""
+    _bf16_2d(out, "out")
+    if ws.dtype != torch.float32 or ws.dim() != 3 or not ws.is_contiguous() or ws.shape[2] != out.shape[1] \
+            or row0 + out.shape[0] > ws.shape[1]:
+        raise RuntimeError("bya_b200.splitk_finalize: ws must be contiguous fp32 [splits, M, N] covering the rows of out")
+    _bya.splitk_finalize(ws, row0, bias, act, out)
+    _count()
+    return out
+
+
+def layernorm_leakyrelu(x, out, gamma, beta, eps=1e-5, slope=0.01):
+    _bf16_2d(x, "x"), _bf16_2d(out, "out")
+    _bya.layernorm_leakyrelu(x, out, float(eps), gamma, beta, float(slope))
+    _count()
+    return out
+
+
+def kv_pack(x, k_off, v_off, K, Vt):
+    """x [G*32, ld] -> K [G,H,32,d], Vt [G,H,d,32] (contiguous bf16)."""
+    _bf16_2d(x, "x")
+    G, H, n, d = K.shape
+    if n != 32 or tuple(Vt.shape) != (G, H, d, 32) or x.shape[0] != G * 32 or not (K.is_contiguous() and Vt.is_contiguous()) \
+            or K.dtype != torch.bfloat16 or Vt.dtype != torch.bfloat16:
+        raise RuntimeError("bya_b200.kv_pack: shape mismatch")
+    _bya.kv_pack(x, k_off, v_off, K, Vt)
+    _count()
+    return K, Vt
+
+
+def router_keys_scatter(k, mat, chars, heads, head_dim):
+    _bf16_2d(k, "k"), _bf16_2d(mat, "mat")
+    if tuple(mat.shape) != (chars * 32 * heads, heads * head_dim) or not mat.is_contiguous() or k.shape[0] != chars * 32:
+        raise RuntimeError("bya_b200.router_keys_scatter: shape mismatch")
+    _bya.router_keys_scatter(k, mat, chars, heads, head_dim)
+    _count()
+    return mat

@@ -32,8 +32,9 @@ int bya_check_device(void);
  * Replaces every nn.Linear on the path: transformer.py:200-221 (attn1 / ff), router.py:226-228, :301-302, :430-466,
  * audio_model.py:179-185, plus the elementwise ops that follow them in the reference (see epilogue modes). */
 enum { GEMM_EPI_STORE = 0, GEMM_EPI_RESIDUAL = 1, GEMM_EPI_QKV = 2,
-       GEMM_EPI_SPLITK_F32 = 3 /* out is an fp32 [M, ldc] workspace (zero before the call): every k-split ADDS its partial
-                                  product with red.global.add.f32; bias / act are applied by bya_splitk_finalize */ };
+       GEMM_EPI_SPLITK_F32 = 3 /* out is an fp32 [split_k][M][ldc] workspace: k-split s STORES its partial product into
+                                  slice s; bya_splitk_finalize sums the slices in a fixed order (deterministic) and
+                                  applies bias / act */ };
 enum { GEMM_ACT_NONE = 0, GEMM_ACT_GELU_TANH = 1, GEMM_ACT_GELU_ERF = 2, GEMM_ACT_RELU = 3 };
 
 typedef struct ByaGemmArgs {
@@ -168,9 +169,10 @@ int bya_audio_weights(void* stream, const float* af, const float* routing, float
 int bya_copy2d(void* stream, const void* src, long long lds, int src_f32, void* out, long long ldo, int rows, int cols);
 /* Zero `bytes` bytes (a memset node, no kernel): split-K workspaces, padded operand tails. */
 int bya_memset_zero(void* stream, void* ptr, long long bytes);
-/* out[r, c] = act(ws[r, c] + bias[c]) as bf16, then ws[r, c] = 0 (ready for the next split-K GEMM). act: GEMM_ACT_* */
-int bya_splitk_finalize(void* stream, float* ws, long long ldw, const void* bias, int act, void* out, long long ldo, int rows,
-                        int cols);
+/* out[r, c] = act(sum_s ws[s][row0 + r][c] + bias[c]) as bf16 for r < rows: ws is the [splits][ws_rows][ldw] workspace a
+ * GEMM_EPI_SPLITK_F32 call filled; (row0, rows) selects a row range of it.  act: GEMM_ACT_* */
+int bya_splitk_finalize(void* stream, const float* ws, int splits, int ws_rows, long long ldw, int row0, const void* bias,
+                        int act, void* out, long long ldo, int rows, int cols);
 /* LayerNorm(dim 1024, affine) followed by LeakyReLU(0.01): the `Linear -> LayerNorm -> LeakyReLU` stages of
  * LocalFacialExtractor's mapping MLPs (router.py:118-154). */
 int bya_layernorm_leakyrelu(void* stream, const void* x, int ldx, void* out, int ldo, int rows, int dim, float eps,

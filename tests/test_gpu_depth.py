@@ -34,6 +34,8 @@ def _check(res, min_cos, max_rel):
           f"(torch-bf16 {o['rel_max_bf16']:.4f});  worst tap {worst[0]}: {worst[1]}")
     assert o["cos"] >= min_cos, o
     assert o["rel_max"] <= max_rel, o
+    for k in ("face_tokens", "audio_ctx"):      # the per-generation prologue (own kernels)
+        assert res["taps"][k]["cos"] >= 0.9995 and res["taps"][k]["rel_max"] <= 0.03, (k, res["taps"][k])
     for k, r in res["taps"].items():
         if k.endswith(".video"):
             assert r["cos"] >= min_cos, (k, r)

@@ -413,6 +413,130 @@ def test_router_small_attention_and_head(ops):
     assert float((r - ref).abs().max()) < 1e-4
 
 
+# ------------------------------------------------------------------------------------------------ prologue kernels (N2)
+def test_copy2d_cast_strides_broadcast_and_overlapping_windows(ops):
+    torch.manual_seed(31)
+    src = torch.randn(37, 200, device=dev)
+    out = torch.zeros(37, 256, device=dev, dtype=torch.bfloat16)
+    ops.copy2d(src[:, 8:136], out[:, 64:192])                       # fp32 -> bf16, strided both sides, vector path
+    assert torch.equal(out[:, 64:192], src[:, 8:136].bfloat16()) and float(out[:, :64].abs().max()) == 0
+    ops.copy2d(src[:, 3:10].bfloat16(), out[:, 1:8])                # unaligned, scalar path
+    assert torch.equal(out[:, 1:8], src[:, 3:10].bfloat16())
+    row = rnd(1, 512)
+    big = torch.zeros(5, 3, 512, device=dev, dtype=torch.bfloat16)
+    ops.copy2d(row.expand(5, 512), big.view(5, 1536)[:, 512:1024])  # broadcast (row stride 0) into a column block
+    assert torch.equal(big[:, 1], row.expand(5, 512)) and float(big[:, 0].abs().max()) == 0
+    a = rnd(53 * 96)                                                 # sliding windows of 5 frames, stride 1 frame
+    win = torch.as_strided(a, (49, 5 * 96), (96, 1))
+    w = torch.empty(49, 480, device=dev, dtype=torch.bfloat16)
+    ops.copy2d(win, w)
+    assert torch.equal(w, a.view(53, 96).unfold(0, 5, 1).permute(0, 2, 1).reshape(49, 480))
+
+
+@pytest.mark.parametrize("M,N,K,split,act", [(98, 512, 46080, 148, 3), (48, 24576, 4096, 3, 0), (24, 768, 1024, 5, 0), (130, 256, 640, 64, 1)])
+def test_gemm_split_k_is_deterministic_and_matches_fp32(ops, M, N, K, split, act):
+    """The skinny weight-streaming GEMMs of the prologue (AudioProjModel.proj1 and the Conv1d(k=2,s=2) taken as a GEMM,
+    audio_model.py:78-114): k-splits as independent tiles, per-split fp32 slices, ordered reduction in the finalize."""
+    torch.manual_seed(32)
+    a, w, b = rnd(M, K, s=0.5), rnd(N, K, s=0.02), rnd(N, s=0.1)
+    split = min(split, K // 64)
+    ws = torch.full((split, M, N), float("nan"), device=dev)
+    out = torch.empty(M + 3, N, device=dev, dtype=torch.bfloat16)
+    outs = []
+    for _ in range(2):
+        ops.gemm(a, w, ws, mode=ops.EPI_SPLITK_F32, split_k=split)
+        ops.splitk_finalize(ws, b, act, out[3:])
+        outs.append(out[3:].clone())
+    assert torch.equal(outs[0], outs[1])
+    ref = a.float() @ w.float().t() + b.float()
+    ref = F.relu(ref) if act == 3 else F.gelu(ref, approximate="tanh") if act == 1 else ref
+    assert rel(outs[0], ref) < TOL
+    half = torch.empty(M // 2, N, device=dev, dtype=torch.bfloat16)  # a row range of the workspace
+    ops.splitk_finalize(ws, b, act, half, row0=M - M // 2)
+    assert torch.equal(half, outs[0][M - M // 2:])
+
+
+def test_gemm_relu_and_layernorm_leakyrelu(ops):
+    torch.manual_seed(33)
+    a, w, b = rnd(98, 512, s=0.5), rnd(512, 512, s=0.05), rnd(512, s=0.1)
+    out = torch.empty(98, 512, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, bias=b, act=ops.ACT_RELU)
+    assert rel(out, F.relu(a.float() @ w.float().t() + b.float())) < TOL
+    x, g, be = rnd(1155, 1024, s=2.0) + 0.3, rnd(1024), rnd(1024, s=0.2)
+    y = torch.empty_like(x)
+    ops.layernorm_leakyrelu(x, y, g, be, eps=1e-5, slope=0.01)
+    assert rel(y, F.leaky_relu(F.layer_norm(x.float(), (1024,), g.float(), be.float(), 1e-5), 0.01)) < TOL
+
+
+@pytest.mark.parametrize("G,H,d", [(2, 16, 128), (26, 48, 64), (3, 5, 64)])
+def test_kv_pack_and_router_keys_scatter(ops, G, H, d):
+    torch.manual_seed(34)
+    x = rnd(G * 32, 2 * H * d + 64)
+    K = torch.empty(G, H, 32, d, device=dev, dtype=torch.bfloat16)
+    Vt = torch.empty(G, H, d, 32, device=dev, dtype=torch.bfloat16)
+    ops.kv_pack(x, 64, 64 + H * d, K, Vt)
+    k = x[:, 64:64 + H * d].view(G, 32, H, d).permute(0, 2, 1, 3)
+    v = x[:, 64 + H * d:].view(G, 32, H, d).permute(0, 2, 3, 1)
+    assert torch.equal(K, k) and torch.equal(Vt, v)
+    if d == 128:   # routed keys -> block-structured score matrix (bya_b200.modules.MultiIPRouter.router_keys layout)
+        kk = x[:, :H * d]
+        mat = torch.full((G * 32 * H, H * d), 7.0, device=dev, dtype=torch.bfloat16)
+        ops.router_keys_scatter(kk, mat, G, H, d)
+        ref = torch.zeros(G, 32, H, H, d, device=dev, dtype=torch.bfloat16)
+        idx = torch.arange(H, device=dev)
+        ref[:, :, idx, idx] = kk.reshape(G, 32, H, d)
+        assert torch.equal(mat, ref.view(G * 32 * H, H * d))
+
+
+def test_prologue_on_own_kernels_vs_oracle_and_torch_modules(built):
+    """LocalFacialExtractor, AudioProjModel (incl. the 1.2 B-parameter conv as a split-K GEMM) and the K/V
+    precompute on libbya.so vs the fp32 oracle (`restated.facial_extractor` / `audio_context`) and vs the torch forward of
+    the host-side module mirrors; CFG batch 2 x 2 characters through one batch; deterministic."""
+    import bya_b200  # noqa: F401
+    from bya_b200.synth import CONFIGS, fill_module, make_inputs
+    from bya_b200.transformer import BindyouravatarTransformer3DModel
+    from oracle import restated
+    import dataclasses
+
+    def cosine(a, b):
+        a, b = a.flatten().double(), b.flatten().double()
+        return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+    cfg = dataclasses.replace(CONFIGS["c1"], num_layers=2, batch=2)
+    with torch.device("meta"):
+        m = BindyouravatarTransformer3DModel(**cfg.ctor_kwargs())
+    m = m.to(torch.bfloat16).to_empty(device="cuda").eval()
+    m.router.frames, m.router.height, m.router.width = cfg.frames, cfg.grid_w, cfg.grid_h
+    m.router.pos_emb = m.router._create_positional_embedding().to("cuda", torch.bfloat16)
+    fill_module(m, 0)
+    inp = make_inputs(cfg, 77, device="cuda", dtype=torch.bfloat16)
+    eng = m.engine()
+    pro = eng.prologue(inp["id_cond"], inp["id_vit_hidden"], inp["audio_embeds"], cfg.frames, True)
+    snap = {k: (v.clone() if torch.is_tensor(v) else [[t.clone() for t in l] for l in v]) for k, v in pro.items()}
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    B, C = 2, cfg.chars
+    face_ref = torch.stack([restated.facial_extractor(sd, inp["id_cond"][c].float(), [v.float() for v in inp["id_vit_hidden"][c]])
+                            for c in range(C)], 1)
+    assert tuple(pro["face_tokens"].shape) == (B, C, 32, 2048)
+    assert cosine(pro["face_tokens"], face_ref) >= 0.9995
+    assert rel(pro["face_tokens"], face_ref) < 0.03
+    a = inp["audio_embeds"].float()
+    ctx_ref = restated.audio_context(sd, a.reshape(B * C, *a.shape[2:]), cfg.frames).reshape(B, C, cfg.frames, 32, -1)
+    assert cosine(pro["audio_ctx"], ctx_ref) >= 0.9995 and rel(pro["audio_ctx"], ctx_ref) < 0.03
+    # K / V^T / routed keys: the torch forward of the module mirrors on the SAME (kernel-produced) tokens
+    for b in range(B):
+        for j in (0, len(m.perceiver_cross_attention) - 1):
+            k, v = m.perceiver_cross_attention[j].face_kv(pro["face_tokens"][b])
+            assert rel(pro["face_k"][b][j], k) < TOL and rel(pro["face_vt"][b][j], v.transpose(-1, -2)) < TOL
+            assert rel(pro["kmat"][b][j], m.router.router_keys(k, j)) < 1.5e-2
+        for l in (0, len(m.audio_model.layers) - 1):
+            k, vt = m.audio_model.audio_kv(pro["audio_ctx"][b], l)
+            assert rel(pro["aud_k"][b][l], k) < TOL and rel(pro["aud_vt"][b][l], vt) < TOL
+    again = eng.prologue(inp["id_cond"], inp["id_vit_hidden"], inp["audio_embeds"], cfg.frames, True)
+    assert torch.equal(again["face_tokens"], snap["face_tokens"]) and torch.equal(again["audio_ctx"], snap["audio_ctx"])
+    assert all(torch.equal(x, y) for x, y in zip(again["aud_k"][1], snap["aud_k"][1]))
+
+
 # ------------------------------------------------------------------------------------------------ bit-exact mask path
 def _c_oracle(masks, Fr, gh, gw, frame_or=False):
     import ctypes
