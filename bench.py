@@ -536,6 +536,10 @@ def main():
                        "cross-attention, prologue recomputed every step",
                        "parallelism": "single GPU" if world == 1 else (f"cfg2 x ulysses sp{world // 2}" if args.cfg_parallel
                                                                        else f"ulysses sp{world}"),
+                       "exchange": None if world == 1 else getattr(model.engine(), "sp_exchange", "nccl") + (
+                           " (NVLink peer memory: QKV / attention epilogues store into the consumer rank, router exchanges "
+                           "pulled by one kernel, device-side epoch barrier)" if getattr(model.engine(), "sp_exchange", "") == "peer"
+                           else " (all_to_all_single)"),
                        "launch": "one CUDA graph per step" if model.use_cuda_graph else "eager (one ctypes call per kernel)",
                        "l2": "working set (17 GB of weights + >1 GB activations per step) exceeds the 126 MB L2; no flush needed",
                        "weights": "random-init, seeded (bya_b200.synth)"},

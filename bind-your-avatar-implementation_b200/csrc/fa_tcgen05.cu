@@ -60,6 +60,10 @@ struct FaArgs {
   int ldo;        // row stride of O in elements
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* out;
+  // PUSH exchange of sequence parallelism (rows_per_peer > 0): row n is stored to out_peers[n / rows_per_peer] at local
+  // row n % rows_per_peer — the owner rank's out-projection operand, possibly over NVLink — instead of `out`
+  __nv_bfloat16* out_peers[BYA_MAX_PEERS];
+  int rows_per_peer;
   long long* trace;   // debug (BYA_FA_TRACE): [32 iterations][16 events] clock64 stamps of CTA (0,0,0), else NULL
 };
 
@@ -166,7 +170,7 @@ BYA_DEVICE void ex2_poly2(float& y0, float& y1, float x0, float x1) {
 template <int POLY16, bool BOUNDED, int NT, int QT>
 __global__ void __launch_bounds__(fa_threads(QT, NT), QT == 1 ? 2 : 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-              const __grid_constant__ CUtensorMap tmap_v, const FaArgs p) {
+              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ FaArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int FA_STAGES = fa_stages(QT);
@@ -542,7 +546,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const int qrow = q0 + t * FA_BM + q * 32 + lane;
     if (qrow < p.seq) {
       const float inv = 1.0f / l;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + size_t(row_base + qrow) * p.ldo + col + h * OC);
+      __nv_bfloat16* orow = p.rows_per_peer > 0
+                                ? p.out_peers[qrow / p.rows_per_peer] + size_t(qrow % p.rows_per_peer) * p.ldo
+                                : p.out + size_t(row_base + qrow) * p.ldo;
+      uint4* dst = reinterpret_cast<uint4*>(orow + col + h * OC);
 #pragma unroll
       for (int i = 0; i < OC / 8; ++i) {
         uint4 v;
@@ -602,8 +609,12 @@ static FaKernel fa_pick_kernel(int qt, int* threads) {
 
 template <bool BOUNDED>
 static int fa_launch(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo, int batch,
-                     int seq, int seq_stride, int heads, float scale) {
-  if (!q || !k || !v || !out || batch <= 0 || seq <= 0 || heads <= 0 || seq_stride < seq) return BYA_ERR_SHAPE;
+                     int seq, int seq_stride, int heads, float scale, void* const* out_peers = nullptr, int n_peers = 0,
+                     int rows_per_peer = 0) {
+  if (!q || !k || !v || (!out && !out_peers) || batch <= 0 || seq <= 0 || heads <= 0 || seq_stride < seq) return BYA_ERR_SHAPE;
+  if (out_peers && (n_peers < 1 || n_peers > BYA_MAX_PEERS || rows_per_peer <= 0 || batch != 1 ||
+                    (long long)n_peers * rows_per_peer < seq))
+    return BYA_ERR_SHAPE;
   if (ld % 8 || ldo % 8 || ld < heads * FA_D || ldo < heads * FA_D) return BYA_ERR_ALIGN;
   const uint64_t rows = uint64_t(batch - 1) * seq_stride + seq;
   // Short sequences (the router's 1 350-token frames): one 128-row query tile per CTA and two CTAs per SM — a CTA only
@@ -638,6 +649,12 @@ static int fa_launch(void* stream, const void* q, const void* k, const void* v, 
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.rows_per_peer = out_peers ? rows_per_peer : 0;
+  for (int i = 0; i < BYA_MAX_PEERS; ++i)
+    a.out_peers[i] = (out_peers && i < n_peers) ? reinterpret_cast<__nv_bfloat16*>(out_peers[i]) : nullptr;
+  if (out_peers)
+    for (int i = 0; i < n_peers; ++i)
+      if (!out_peers[i] || (reinterpret_cast<uintptr_t>(out_peers[i]) & 15)) return BYA_ERR_ALIGN;
   static long long* trace = nullptr;   // debug timeline buffer (tools/gpu_fa_trace.py), looked up once
   static bool trace_looked_up = false;
   if (!trace_looked_up) {
@@ -660,6 +677,16 @@ extern "C" int bya_attention_d64(void* stream, const void* q, const void* k, con
 extern "C" int bya_attention_d64_strided(void* stream, const void* q, const void* k, const void* v, int ld, void* out,
                                          int ldo, int batch, int seq, int seq_stride, int heads, float scale) {
   return bya::fa_launch<false>(stream, q, k, v, ld, out, ldo, batch, seq, seq_stride, heads, scale);
+}
+
+extern "C" int bya_attention_d64_scatter(void* stream, const void* q, const void* k, const void* v, int ld, void* const* out_peers,
+                                         int n_peers, int rows_per_peer, int ldo, int seq, int heads, float scale,
+                                         float score_bound_log2) {
+  if (score_bound_log2 > 0.f) {
+    if (score_bound_log2 > 64.f) return BYA_ERR_SHAPE;
+    return bya::fa_launch<true>(stream, q, k, v, ld, nullptr, ldo, 1, seq, seq, heads, 1.0f, out_peers, n_peers, rows_per_peer);
+  }
+  return bya::fa_launch<false>(stream, q, k, v, ld, nullptr, ldo, 1, seq, seq, heads, scale, out_peers, n_peers, rows_per_peer);
 }
 
 extern "C" int bya_attention_d64_bounded(void* stream, const void* q, const void* k, const void* v, int ld, void* out,

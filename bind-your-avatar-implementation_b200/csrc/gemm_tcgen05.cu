@@ -57,10 +57,15 @@ __device__ long long* g_gemm_trace = nullptr;
     if (g_gemm_trace && blockIdx.x == 0 && (i) < 16 && lane == 0) g_gemm_trace[(i) * 8 + (e)] = clock64(); \
   } while (0)
 
+// store maps of the sequence-parallel PUSH exchange: one 2-D [M, col_block] map per destination rank (peer memory)
+struct alignas(64) PeerMaps {
+  CUtensorMap m[BYA_MAX_PEERS];
+};
+
 template <int BN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_c, const GemmArgs p) {
+                 const __grid_constant__ CUtensorMap tmap_c, const GemmArgs p, const __grid_constant__ PeerMaps pmaps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = GemmSmem<BN, CTAS>;
@@ -270,8 +275,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.col_block) tma_store_3d(&tmap_c, stg, col % p.col_block, row0, col / p.col_block);
-          else tma_store_2d(&tmap_c, stg, col, row0);
+          if (p.col_block) {
+            if (p.peer_out[0]) tma_store_2d(&pmaps.m[col / p.col_block], stg, col % p.col_block, row0);   // NVLink push
+            else tma_store_3d(&tmap_c, stg, col % p.col_block, row0, col / p.col_block);
+          } else {
+            tma_store_2d(&tmap_c, stg, col, row0);
+          }
           tma_store_commit();
         }
       };
@@ -447,7 +456,20 @@ static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W,
   rc = bya_host::encode_tmap_bf16(&tb, W, a.K, a.N, uint64_t(ldw) * 2, BK, L::kBRows);
   if (rc) return rc;
   CUtensorMap tc;   // output: 32 x 32 boxes; with col_block a 3-D [dest][row][col] view of the send buffer
-  if (a.mode == GEMM_EPI_SPLITK_F32) tc = ta;   // fp32 workspace, written with plain vector stores: no store map
+  static PeerMaps pm_none = {};
+  PeerMaps pm_local;
+  const PeerMaps* pm = &pm_none;
+  if (a.col_block && a.peer_out[0]) {
+    const int nd = a.N / a.col_block;
+    for (int d = 0; d < nd; ++d) {
+      if (!a.peer_out[d]) return BYA_ERR_SHAPE;
+      rc = bya_host::encode_tmap_bf16(&pm_local.m[d], a.peer_out[d], a.col_block, a.M, uint64_t(a.ldc) * 2, 32, 32);
+      if (rc) return rc;
+    }
+    for (int d = nd; d < BYA_MAX_PEERS; ++d) pm_local.m[d] = pm_local.m[0];
+    pm = &pm_local;
+  }
+  if (a.mode == GEMM_EPI_SPLITK_F32 || pm != &pm_none) tc = ta;   // no local store map (fp32 workspace / peer stores)
   else
     rc = a.col_block ? bya_host::encode_tmap_bf16(&tc, a.out, a.col_block, a.M, uint64_t(a.ldc) * 2, 32, 32, a.N / a.col_block,
                                                   uint64_t(a.col_block_stride) * 2)
@@ -471,7 +493,7 @@ static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W,
   const int num_tiles = ((a.M + BM * CTAS - 1) / (BM * CTAS)) * (a.N / BN) * (a.split_k > 1 ? a.split_k : 1);
   if constexpr (CTAS == 1) {
     const int grid = num_tiles < bya_host::num_sms() ? num_tiles : bya_host::num_sms();
-    kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, tc, a);
+    kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, tc, a, *pm);
   } else {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -494,7 +516,7 @@ static int launch_gemm(const GemmArgs& a, const void* A, int lda, const void* W,
     }
     const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
     cfg.gridDim = dim3(2 * pairs);
-    if (cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, a) != cudaSuccess) return BYA_ERR_CUDA;
+    if (cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, a, *pm) != cudaSuccess) return BYA_ERR_CUDA;
   }
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }
@@ -527,6 +549,7 @@ extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W
   }
   if (a.col_block && (a.col_block % 64 || a.N % a.col_block || a.col_block_stride % 8 || a.mode == GEMM_EPI_RESIDUAL))
     return BYA_ERR_SHAPE;
+  if (a.peer_out[0] && (!a.col_block || a.N / a.col_block > BYA_MAX_PEERS)) return BYA_ERR_SHAPE;
   if (a.mode == GEMM_EPI_SPLITK_F32) {
     if (a.col_block || a.ldc % 4 || (reinterpret_cast<uintptr_t>(a.out) & 15)) return BYA_ERR_SHAPE;
     if (a.split_k < 1) a.split_k = 1;
@@ -535,7 +558,7 @@ extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W
     a.split_k = 0;
   }
   if (a.a_kblock == a.K) a.a_kblock = 0;
-  if (a.col_block == a.N) a.col_block = 0;   // a single column block is the plain layout
+  if (a.col_block == a.N && !a.peer_out[0]) a.col_block = 0;   // a single column block is the plain layout
   if (a.a_kblock && (a.a_kblock % BK || a.K % a.a_kblock || a.a_kblock_stride % 8)) return BYA_ERR_SHAPE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int force = gemm_ctas_override();

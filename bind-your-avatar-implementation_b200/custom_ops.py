@@ -45,10 +45,10 @@ def _op(schema: str):
 @_op("gemm_bf16(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int act, int mode, Tensor? resid, Tensor? gate_a, "
      "Tensor? gate_b, int split_row, float alpha, Tensor? row_bias_scale, int qkv_block, float ln_eps, Tensor? rope_cos, "
      "Tensor? rope_sin, int rope_row0, Tensor? nq_w, Tensor? nq_b, Tensor? nk_w, Tensor? nk_b, int group_m, int col_block, "
-     "int col_block_stride, int a_kblock, int a_kblock_stride, float q_premul, int split_k) -> ()")
+     "int col_block_stride, int a_kblock, int a_kblock_stride, float q_premul, int split_k, Tensor[]? peer_out) -> ()")
 def _gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, alpha, row_bias_scale, qkv_block, ln_eps,
                rope_cos, rope_sin, rope_row0, nq_w, nq_b, nk_w, nk_b, group_m, col_block, col_block_stride, a_kblock,
-               a_kblock_stride, q_premul, split_k):
+               a_kblock_stride, q_premul, split_k, peer_out):
     g = ByaGemmArgs()
     g.M, g.N, g.K = a.shape[0], w.shape[0], w.shape[1]
     g.mode, g.act, g.group_m = mode, act, group_m
@@ -64,6 +64,9 @@ def _gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, alp
     g.a_kblock, g.a_kblock_stride = a_kblock, a_kblock_stride
     g.q_premul = q_premul
     g.split_k = split_k
+    if peer_out:   # push exchange: column block d goes to peer_out[d] (another GPU's memory), see include/bya.h
+        for d, t in enumerate(peer_out):
+            g.peer_out[d] = t.data_ptr()
     check(lib().bya_gemm_bf16(_stream(), _ptr(a), a.stride(0), _ptr(w), w.stride(0), ctypes.byref(g)), "gemm")
 
 
@@ -82,6 +85,16 @@ def _attention_d64(q, k, v, out, batch, seq, seq_stride, heads, scale, score_bou
         rc = L.bya_attention_d64(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(out), out.stride(0), batch, seq, heads,
                                  ctypes.c_float(scale))
     check(rc, "attention_d64")
+
+
+@_op("attention_d64_scatter(Tensor q, Tensor k, Tensor v, Tensor[] out_peers, int rows_per_peer, int seq, int heads, float scale, "
+     "float score_bound_log2) -> ()")
+def _attention_d64_scatter(q, k, v, out_peers, rows_per_peer, seq, heads, scale, score_bound_log2):
+    n = len(out_peers)
+    arr = (ctypes.c_void_p * n)(*[t.data_ptr() for t in out_peers])
+    rc = lib().bya_attention_d64_scatter(_stream(), _ptr(q), _ptr(k), _ptr(v), q.stride(0), arr, n, rows_per_peer,
+                                         out_peers[0].stride(0), seq, heads, ctypes.c_float(scale), ctypes.c_float(score_bound_log2))
+    check(rc, "attention_d64_scatter")
 
 
 @_op("layernorm_modulate(Tensor x, Tensor(a!) out, float eps, Tensor? gamma, Tensor? beta, Tensor? scale_a, Tensor? shift_a, "
@@ -222,3 +235,14 @@ def _kv_pack(x, k_off, v_off, K, Vt):
 def _router_keys_scatter(k, mat, chars, heads, head_dim):
     check(lib().bya_router_keys_scatter(_stream(), _ptr(k), ctypes.c_longlong(k.stride(0)), _ptr(mat), chars, heads, head_dim),
           "router_keys_scatter")
+
+
+# ---------------------------------------------------------------- exchanges over NVLink peer memory
+@_op("peer_barrier(Tensor(a!) counter, Tensor flag_ptrs, int my_rank, int n_ranks) -> ()")
+def _peer_barrier(counter, flag_ptrs, my_rank, n_ranks):
+    check(lib().bya_peer_barrier(_stream(), _ptr(counter), _ptr(flag_ptrs), my_rank, n_ranks), "peer_barrier")
+
+
+@_op("peer_pull(Tensor segs, int n_segs, Tensor src_ptrs, Tensor(a!) dst, int vec_bytes, int blocks_per_seg) -> ()")
+def _peer_pull(segs, n_segs, src_ptrs, dst, vec_bytes, blocks_per_seg):
+    check(lib().bya_peer_pull(_stream(), _ptr(segs), n_segs, _ptr(src_ptrs), _ptr(dst), vec_bytes, blocks_per_seg), "peer_pull")

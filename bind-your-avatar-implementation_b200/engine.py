@@ -161,12 +161,16 @@ class RouterShard:
                             b=qkv_rows_by_destination(d["s_qkv_b"], 512, world)) for d in rp.blocks]
 
 
-def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all: torch.Tensor, kmat: torch.Tensor, layer: int,
-                  chars: int, out: torch.Tensor, group) -> torch.Tensor:
-    """`run_router` sharded over the sequence-parallel group: q_all [Nv,2048] (every rank holds all face queries) ->
-    out [Nv,C] fp32 on every rank.  Same kernels, same per-row arithmetic as the single-GPU router."""
+def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: torch.Tensor, layer: int,
+                  chars: int, out: torch.Tensor, group, peer=None, q_ptrs=None, text_len: int = 0, rows_per_rank: int = 0) -> torch.Tensor:
+    """`run_router` sharded over the sequence-parallel group: q_all [Nv,2048] (every rank holds all face queries; None with
+    the peer exchange, which pulls this rank's rows from their owners) -> out [Nv,C] fp32 on every rank.  Same kernels, same
+    per-row arithmetic as the single-GPU router.  Exchanges: NCCL all-to-all + permuting copies (peer=None), or one device
+    barrier + one strided pull from the peers' buffers each (`peer.py`; the position gather / scatter permutations are
+    folded into the segment strides)."""
     import torch.distributed as dist
 
+    from . import peer as pk
     from .sp import router_gather_positions, router_scatter_positions
 
     C, Fr, P, hwl, hl = chars, rs.frames, rs.P, rs.hwl, rs.hl
@@ -175,7 +179,12 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all: torch.
     CF = C * Fr
     Ws, Wo = 3 * hl * 64, hl * 64
     qf = ws.get("rs_qsel", (R, 2048))
-    torch.index_select(q_all, 0, rs.idx, out=qf)
+    if peer is None:
+        torch.index_select(q_all, 0, rs.idx, out=qf)
+    else:
+        peer.barrier()           # every owner's to_q GEMM has written its `face_q`
+        peer.pull(("face_q", Fr, rs.hw, text_len, rows_per_rank), lambda: pk.face_query_segments(
+            P, rs.rank, Fr, rs.hw, text_len, rows_per_rank, 2048), q_ptrs, qf, blocks_per_seg=4)
     rq = ws.get("rs_q", (R, 2048))
     ops.layernorm_modulate(qf, rq, eps=rp.eps, gamma=rp.nq_w, beta=rp.nq_b)
     rq2 = ws.get("rs_q2", (R, 2048))
@@ -189,22 +198,36 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all: torch.
     xn = ws.get("rs_xn", (M, 512))
     qkv = ws.get("rs_qkv", (M, 1536))
     att = ws.get("rs_att", (M, 512))
-    s_send = ws.get("rs_s_send", (P, M, Ws))          # [dest][local row][q|k|v heads of dest]
-    s_recv = ws.get("rs_s_recv", (P, M, Ws))          # [src][(c,f), src's positions][my heads]
     s_full = ws.get("rs_s_full", (CF * rs.hw_pad, Ws))   # [(c,f)][all positions (padded)][my heads]
-    s_att = ws.get("rs_s_att", (CF * rs.hw_pad, Wo))
-    o_send = ws.get("rs_o_send", (P, M, Wo))
     o_recv = ws.get("rs_o_recv", (P, M, Wo))          # [src heads][local row] = K-blocked A of the out-projection
+    if peer is None:
+        s_send = ws.get("rs_s_send", (P, M, Ws))          # [dest][local row][q|k|v heads of dest]
+        s_recv = ws.get("rs_s_recv", (P, M, Ws))          # [src][(c,f), src's positions][my heads]
+        s_att = ws.get("rs_s_att", (CF * rs.hw_pad, Wo))
+        o_send = ws.get("rs_o_send", (P, M, Wo))
+    else:
+        s_send, _, s_send_ptrs = peer.get("rs_s_send", (P, M, Ws))
+        s_att, _, s_att_ptrs = peer.get("rs_s_att", (CF * rs.hw_pad, Wo))
     for d, dsp in zip(rp.blocks, rs.blocks):
         # spatial: all H*W tokens of one (character, frame) — heads sharded, positions gathered
         ops.layernorm_modulate(x, xn, eps=d["n1"][2], gamma=d["n1"][0], beta=d["n1"][1])
         ops.gemm(xn, dsp["w"], s_send[0], bias=dsp["b"], col_block=Ws, col_block_stride=M * Ws)
-        dist.all_to_all_single(s_recv, s_send, group=group)
-        s_full.view(CF, P, hwl, Ws).copy_(router_gather_positions(s_recv, CF, P, hwl))
+        if peer is None:
+            dist.all_to_all_single(s_recv, s_send, group=group)
+            s_full.view(CF, P, hwl, Ws).copy_(router_gather_positions(s_recv, CF, P, hwl))
+        else:
+            peer.barrier()
+            peer.pull(("rs_gather", CF, hwl, M, Ws), lambda: pk.router_gather_segments(P, rs.rank, CF, hwl, M, Ws),
+                      s_send_ptrs, s_full)
         ops.attention_d64(s_full[:, :Wo], s_full[:, Wo:2 * Wo], s_full[:, 2 * Wo:], s_att, CF, rs.hw, hl,
                           seq_stride=rs.hw_pad)
-        o_send.view(P, CF, hwl, Wo).copy_(router_scatter_positions(s_att, CF, P, hwl))
-        dist.all_to_all_single(o_recv, o_send, group=group)
+        if peer is None:
+            o_send.view(P, CF, hwl, Wo).copy_(router_scatter_positions(s_att, CF, P, hwl))
+            dist.all_to_all_single(o_recv, o_send, group=group)
+        else:
+            peer.barrier()
+            peer.pull(("rs_scatter", CF, hwl, M, Wo), lambda: pk.router_scatter_segments(P, rs.rank, CF, hwl, M, Wo),
+                      s_att_ptrs, o_recv)
         ops.gemm(o_recv[0], d["s_o_w"], x, bias=d["s_o_b"], mode=ops.EPI_RESIDUAL, resid=x, a_kblock=Wo,
                  a_kblock_stride=M * Wo)
         # temporal: the F tokens at one (character, local position)
@@ -221,11 +244,17 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all: torch.
         ops.layernorm_modulate(x, xn, eps=d["n4"][2], gamma=d["n4"][0], beta=d["n4"][1])
         ops.gemm(xn, d["m0_w"], att, bias=d["m0_b"], act=ops.ACT_GELU_ERF)
         ops.gemm(att, d["m2_w"], x, bias=d["m2_b"], mode=ops.EPI_RESIDUAL, resid=x)
-    r_loc = ws.get("rs_r_loc", (R, C), torch.float32)
-    ops.router_head(x, rp.head_w, rp.head_b, r_loc, R, C)
-    r_all = ws.get("rs_r_all", (P, Fr, hwl, C), torch.float32)
-    dist.all_gather_into_tensor(r_all, r_loc, group=group)
-    out.view(Fr, rs.hw, C).copy_(r_all.permute(1, 0, 2, 3).reshape(Fr, rs.hw_pad, C)[:, :rs.hw])
+    if peer is None:
+        r_loc = ws.get("rs_r_loc", (R, C), torch.float32)
+        ops.router_head(x, rp.head_w, rp.head_b, r_loc, R, C)
+        r_all = ws.get("rs_r_all", (P, Fr, hwl, C), torch.float32)
+        dist.all_gather_into_tensor(r_all, r_loc, group=group)
+        out.view(Fr, rs.hw, C).copy_(r_all.permute(1, 0, 2, 3).reshape(Fr, rs.hw_pad, C)[:, :rs.hw])
+    else:
+        r_loc, _, r_ptrs = peer.get("rs_r_loc", (R, C), torch.float32)
+        ops.router_head(x, rp.head_w, rp.head_b, r_loc, R, C)
+        peer.barrier()
+        peer.pull(("rs_routing", Fr, rs.hw, C), lambda: pk.routing_gather_segments(P, Fr, rs.hw, C), r_ptrs, out, blocks_per_seg=2)
     return out
 
 
@@ -381,6 +410,29 @@ class StepEngine:
         for L_ in self.layers:
             L_["w_qkv_sp"] = qkv_rows_by_destination(L_["w_qkv"], self.D, P)
             L_["b_qkv_sp"] = qkv_rows_by_destination(L_["b_qkv"], self.D, P)
+        # exchange mechanism: "peer" = NVLink peer memory (push epilogues + pull kernel + device barrier, peer.py),
+        # "nccl" = all_to_all_single (the baseline); "auto" tries peer memory and says so loudly if it cannot be set up
+        import os
+        import sys
+
+        want = os.environ.get("BYA_SP_EXCHANGE", getattr(self.model, "sp_exchange", "auto"))
+        self.peer = None
+        if want in ("auto", "peer") and P > 1:
+            try:
+                from .peer import PeerGroup
+
+                self.peer = PeerGroup(group, self.device)
+            except Exception as e:   # noqa: BLE001
+                if want == "peer":
+                    raise
+                print(f"bya_b200: NVLink peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-to-all",
+                      file=sys.stderr, flush=True)
+            # every rank must take the same path
+            ok = torch.tensor([1 if self.peer is not None else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.peer = None
+        self.sp_exchange = "peer" if self.peer is not None else "nccl"
 
     def _prologue_cache_key(self, id_cond, id_vit_hidden, audio_embeds, frames, use_router):
         """Identity of the timestep-invariant inputs (the pipeline passes the same tensors on all 50 steps).  The key
@@ -575,13 +627,21 @@ class StepEngine:
         routing = ws.get("routing", (Nv, C), torch.float32)
         aw = ws.get("aud_w", (max(Vl, 1), C), torch.float32)
         awsum = ws.get("aud_wsum", (max(Vl, 1),), torch.float32)
+        pg = getattr(self, "peer", None) if P > 1 else None
         if P == 1:
             qkv = ws.get("qkv", (N, 3 * D))
-        else:
+        elif pg is None:
             qkv_send = ws.get("qkv_send", (P, R, 3 * Dl))   # [dest][local row][q|k|v heads of dest]
             qkv = ws.get("qkv", (N, 3 * Dl))                # after the exchange: every row, this rank's heads
             o_send = ws.get("o_send", (N, Dl))              # attention output of this rank's heads, every row
             o_recv = ws.get("o_recv", (P, R, Dl))           # after the exchange: local rows, [src heads]
+        else:
+            # PUSH exchange: the QKV epilogue stores destination d's [q|k|v] block into rank d's `qkv` rows
+            # [rank*R, (rank+1)*R); the attention epilogue stores row n into its owner's o_recv[rank] — no send buffers
+            qkv, qkv_peers, _ = pg.get("qkv", (N, 3 * Dl))
+            o_recv, o_peers, _ = pg.get("o_recv", (P, R, Dl))
+            qkv_dst = [t[rank * R:(rank + 1) * R] for t in qkv_peers]
+            o_dst = [t[rank] for t in o_peers]
 
         for b in range(B):
             x = x_all[b]
@@ -616,7 +676,7 @@ class StepEngine:
                     ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, 1, N, self.heads, tag="self_attention",
                                       score_bound_log2=sb)
                     ops.gemm(att, L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g, split_row=Tl)
-                else:
+                elif pg is None:
                     ops.gemm(xn, L["w_qkv_sp"], qkv_send[0], bias=L["b_qkv_sp"], mode=ops.EPI_QKV, split_row=Tl,
                              ln_eps=L["qk_eps"], rope=(cos, sin), rope_row0=v0, nq=L["nq"], nk=L["nk"], qkv_block=3 * Dl,
                              col_block=3 * Dl, col_block_stride=R * 3 * Dl, q_premul=qpm)
@@ -624,6 +684,16 @@ class StepEngine:
                     ops.attention_d64(qkv[:, :Dl], qkv[:, Dl:2 * Dl], qkv[:, 2 * Dl:], o_send, 1, N, Hl_, tag="self_attention",
                                       score_bound_log2=sb)
                     dist.all_to_all_single(o_recv, o_send.view(P, R, Dl), group=self.sp_group)
+                    ops.gemm(o_recv[0], L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g,
+                             split_row=Tl, a_kblock=Dl, a_kblock_stride=R * Dl)
+                else:
+                    ops.gemm(xn, L["w_qkv_sp"], qkv_dst[0], bias=L["b_qkv_sp"], mode=ops.EPI_QKV, split_row=Tl,
+                             ln_eps=L["qk_eps"], rope=(cos, sin), rope_row0=v0, nq=L["nq"], nk=L["nk"], qkv_block=3 * Dl,
+                             col_block=3 * Dl, q_premul=qpm, peer_out=qkv_dst)
+                    pg.barrier()      # every rank's q|k|v block has landed in my `qkv`
+                    ops.attention_d64_scatter(qkv[:, :Dl], qkv[:, Dl:2 * Dl], qkv[:, 2 * Dl:], o_dst, R, N, Hl_,
+                                              tag="self_attention", score_bound_log2=sb)
+                    pg.barrier()      # every rank's heads have landed in my o_recv
                     ops.gemm(o_recv[0], L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g,
                              split_row=Tl, a_kblock=Dl, a_kblock_stride=R * Dl)
                 ops.layernorm_modulate(x, xn, eps=L["ln2"][2], gamma=L["ln2"][0], beta=L["ln2"][1], mod_a=(esc2, esh2),
@@ -638,7 +708,10 @@ class StepEngine:
                 if m.is_train_face and i % m.cross_attn_interval == 0 and ca < len(self.face):
                     Fc = self.face[ca]
                     dq = Fc["w_q"].shape[0]
-                    qpad = ws.get("face_q", (R, dq))         # rows [Tl:] hold the local video queries
+                    if pg is not None and use_router and getattr(m, "sp_shard_router", True):
+                        qpad, _, qpad_ptrs = pg.get("face_q", (R, dq))   # peers pull the rows of their router positions
+                    else:
+                        qpad, qpad_ptrs = ws.get("face_q", (R, dq)), None   # rows [Tl:] hold the local video queries
                     qf = qpad[Tl:]
                     if Vl:
                         xnv = xn[:Vl]
@@ -647,15 +720,18 @@ class StepEngine:
                     if use_router:
                         if P == 1:
                             q_all = qf
-                        else:  # every rank needs the queries of its router positions in all frames: gather them
+                        elif qpad_ptrs is None:  # every rank needs the queries of its router positions in all frames: gather them
                             qg = ws.get("face_q_all", (N, dq))
                             dist.all_gather_into_tensor(qg, qpad, group=self.sp_group)
                             q_all = qg[T:]
+                        else:
+                            q_all = None         # pulled from the owners' `face_q` inside run_router_sp
                         if P > 1 and getattr(m, "sp_shard_router", True):
                             rs = self._router_shard
                             if rs is None or (rs.frames, rs.hw, rs.P) != (Fr, hw, P):
                                 rs = self._router_shard = RouterShard(self.router, Fr, hw, P, rank, dev)
-                            run_router_sp(self.router, rs, ws, q_all, pro["kmat"][b][ca], ca, C, routing, self.sp_group)
+                            run_router_sp(self.router, rs, ws, q_all, pro["kmat"][b][ca], ca, C, routing, self.sp_group,
+                                          peer=pg, q_ptrs=qpad_ptrs, text_len=T, rows_per_rank=R)
                         else:
                             run_router(self.router, ws, q_all, pro["kmat"][b][ca], ca, C, Fr, hw, routing)
                         if tap and b == 0:

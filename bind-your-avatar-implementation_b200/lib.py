@@ -24,6 +24,7 @@ class ByaGemmArgs(ctypes.Structure):
         ("col_block", ctypes.c_int), ("col_block_stride", ctypes.c_longlong),
         ("a_kblock", ctypes.c_int), ("a_kblock_stride", ctypes.c_longlong),
         ("q_premul", ctypes.c_float), ("split_k", ctypes.c_int),
+        ("peer_out", ctypes.c_void_p * 8),
     ]
 
 

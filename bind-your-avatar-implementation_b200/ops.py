@@ -49,8 +49,10 @@ def _bf16_2d(t: torch.Tensor, name: str):
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=ACT_NONE, mode=EPI_STORE,
          resid=None, gate_a=None, gate_b=None, split_row=0, alpha=1.0, row_bias_scale=None,
          qkv_block=0, ln_eps=1e-6, rope=None, rope_row0=0, nq=None, nk=None, group_m=0, col_block=0,
-         col_block_stride=0, a_kblock=0, a_kblock_stride=0, q_premul=0.0, split_k=0) -> torch.Tensor:
+         col_block_stride=0, a_kblock=0, a_kblock_stride=0, q_premul=0.0, split_k=0, peer_out=None) -> torch.Tensor:
     """out = epilogue(a @ w.T); a [M,K], w [N,K], out [M,N] (row strides may exceed the width).
+    With peer_out (a list of N/col_block [M, col_block] tensors, possibly views of OTHER ranks' memory): column block d is
+    stored to peer_out[d]; pass out=peer_out[0].
     With a_kblock: `a` is the first [M, a_kblock] block of K/a_kblock blocks a_kblock_stride elements apart.
     With col_block: `out` is the first [M, col_block] block of N/col_block blocks col_block_stride elements apart."""
     global LAUNCHES
@@ -78,7 +80,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
         (nq_w, nq_b), (nk_w, nk_b) = nq, nk
     _bya.gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, float(alpha), row_bias_scale, qkv_block,
                    float(ln_eps), rope_cos, rope_sin, rope_row0, nq_w, nq_b, nk_w, nk_b, group_m, col_block, col_block_stride,
-                   a_kblock, a_kblock_stride, float(q_premul), split_k)
+                   a_kblock, a_kblock_stride, float(q_premul), split_k, peer_out)
     LAUNCHES += 1
     return out
 
@@ -355,3 +357,44 @@ def router_keys_scatter(k, mat, chars, heads, head_dim):
     _bya.router_keys_scatter(k, mat, chars, heads, head_dim)
     _count()
     return mat
+
+
+# ---------------------------------------------------------------- exchanges over NVLink peer memory
+def attention_d64_scatter(q, k, v, out_peers, rows_per_peer, seq, heads, scale=0.125, tag=None, score_bound_log2=None):
+    """Attention of this rank's heads over all `seq` rows; row n is stored to out_peers[n // rows_per_peer][n % rows_per_peer]
+    (tensors [rows_per_peer, heads*64], possibly views of other ranks' memory)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _bf16_2d(t, n)
+        if t.shape[0] != seq or t.shape[1] != heads * 64:
+            raise RuntimeError(f"bya_b200.attention_d64_scatter: {n} has shape {tuple(t.shape)}")
+    if not (q.stride(0) == k.stride(0) == v.stride(0)):
+        raise RuntimeError("bya_b200.attention_d64_scatter: q, k, v must share a row stride")
+    ld = out_peers[0].stride(0)
+    for t in out_peers:
+        _bf16_2d(t, "out_peers")
+        if tuple(t.shape) != (rows_per_peer, heads * 64) or t.stride(0) != ld:
+            raise RuntimeError("bya_b200.attention_d64_scatter: out_peers must be [rows_per_peer, heads*64] with one row stride")
+    if len(out_peers) * rows_per_peer < seq:
+        raise RuntimeError("bya_b200.attention_d64_scatter: the peers do not cover the sequence")
+    ev = _prof(tag)
+    _bya.attention_d64_scatter(q, k, v, list(out_peers), rows_per_peer, seq, heads, float(scale),
+                               float(score_bound_log2) if score_bound_log2 is not None else 0.0)
+    if ev is not None:
+        ev.record()
+    _count()
+
+
+def peer_barrier(counter, flag_ptrs, my_rank, n_ranks):
+    if counter.dtype != torch.int32 or flag_ptrs.dtype != torch.int64 or not counter.is_cuda or not flag_ptrs.is_cuda \
+            or flag_ptrs.numel() < n_ranks:
+        raise RuntimeError("bya_b200.peer_barrier: int32 counter and an int64 pointer table on the device")
+    _bya.peer_barrier(counter, flag_ptrs, my_rank, n_ranks)
+    _count()
+
+
+def peer_pull(segs, n_segs, src_ptrs, dst, vec_bytes, blocks_per_seg=8):
+    if segs.dtype != torch.uint8 or segs.numel() != n_segs * 64 or not segs.is_cuda or src_ptrs.dtype != torch.int64 \
+            or not dst.is_cuda or not dst.is_contiguous():
+        raise RuntimeError("bya_b200.peer_pull: bad segment table / pointer table / destination")
+    _bya.peer_pull(segs, n_segs, src_ptrs, dst, vec_bytes, blocks_per_seg)
+    _count()

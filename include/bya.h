@@ -31,6 +31,7 @@ int bya_check_device(void);
 /* ---------------------------------------------------------------- GEMM  out = epilogue(A[M,K] · W[N,K]^T)
  * Replaces every nn.Linear on the path: transformer.py:200-221 (attn1 / ff), router.py:226-228, :301-302, :430-466,
  * audio_model.py:179-185, plus the elementwise ops that follow them in the reference (see epilogue modes). */
+#define BYA_MAX_PEERS 8
 enum { GEMM_EPI_STORE = 0, GEMM_EPI_RESIDUAL = 1, GEMM_EPI_QKV = 2,
        GEMM_EPI_SPLITK_F32 = 3 /* out is an fp32 [split_k][M][ldc] workspace: k-split s STORES its partial product into
                                   slice s; bya_splitk_finalize sums the slices in a fixed order (deterministic) and
@@ -81,6 +82,10 @@ typedef struct ByaGemmArgs {
    * weight-streaming GEMMs of the per-generation prologue — audio_model.py:78-114: M <= 128 rows against a 2.4 GB
    * weight — need more than N / 256 CTAs to pull HBM bandwidth).  0 / 1 -> off. */
   int split_k;
+  /* Sequence-parallel PUSH exchange (with col_block): when peer_out[0] != NULL, column block d is TMA-stored to
+   * peer_out[d] — the base of a row-major [M, col_block] block with row stride ldc that may live in ANOTHER GPU's memory
+   * (NVLink peer mapping) — instead of out + d * col_block_stride.  N / col_block <= BYA_MAX_PEERS. */
+  void* peer_out[8];
 } ByaGemmArgs;
 
 int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W, int ldw, const ByaGemmArgs* args);
@@ -104,6 +109,14 @@ int bya_attention_d64_strided(void* stream, const void* q, const void* k, const 
  * Returns BYA_ERR_SHAPE if the bound is not in (0, 64]. */
 int bya_attention_d64_bounded(void* stream, const void* q, const void* k, const void* v, int ld, void* out, int ldo,
                               int batch, int seq, int heads, float score_bound_log2);
+
+/* Sequence-parallel PUSH exchange: the attention for this rank's heads over ALL rows, each output row stored straight
+ * into its owner's buffer: row n goes to out_peers[n / rows_per_peer] + (n % rows_per_peer) * ldo + h*64 (the K-blocked A
+ * operand of the owner's out-projection; the pointers may be NVLink peer mappings).  batch 1.  score_bound_log2 > 0
+ * selects the bounded kernel (see above), otherwise `scale` is used. */
+int bya_attention_d64_scatter(void* stream, const void* q, const void* k, const void* v, int ld, void* const* out_peers,
+                              int n_peers, int rows_per_peer, int ldo, int seq, int heads, float scale,
+                              float score_bound_log2);
 
 /* ---------------------------------------------------------------- routed small-KV cross-attention (32 keys)
  * out[n, h*d..] = sum_c w[n,c] * softmax_k(scale * q[n,h,:].K[g][h][k][:]) @ V[g][h],  g = c*kv_frames + n/(tokens/kv_frames)
@@ -186,6 +199,24 @@ int bya_kv_pack(void* stream, const void* x, long long ldx, int k_off, int v_off
  * [chars*32*heads, heads*head_dim]: row (c, tok*heads + h) holds the key of head h in columns h*head_dim.., zeros
  * elsewhere — so that the router's per-head q.k^T (router.py:385-393) is one dense GEMM against it. */
 int bya_router_keys_scatter(void* stream, const void* k, long long ldk, void* mat, int chars, int heads, int head_dim);
+
+/* ---------------------------------------------------------------- exchanges over NVLink peer memory
+ * No reference counterpart (the reference is single-GPU); oracle = the single-GPU result.
+ * bya_peer_barrier: epoch barrier of the sequence-parallel group.  counter: this rank's epoch (device int, zero at start,
+ * advanced by the kernel); peer_flags: device array of n_ranks pointers, peer_flags[r] = rank r's flag array [n_ranks]
+ * (zero at start; peer-mapped).  Returns once every rank of the group has issued the same barrier. */
+int bya_peer_barrier(void* stream, int* counter, int* const* peer_flags, int my_rank, int n_ranks);
+/* bya_peer_pull: gathers n_segs strided 3-D blocks from peer buffers into a local buffer: for each segment, for o < outer,
+ * r < rows: copy row_bytes bytes from peer_src[peer] + src_off + o*src_outer_stride + r*src_row_stride to
+ * dst + dst_off + o*dst_outer_stride + r*dst_row_stride.  All offsets / strides / row_bytes multiples of vec_bytes
+ * (16, 8 or 4).  segs and peer_src are device arrays. */
+typedef struct ByaPullSeg {
+  long long src_off, dst_off;
+  long long src_outer_stride, dst_outer_stride, src_row_stride, dst_row_stride;
+  int peer, outer, rows, row_bytes;
+} ByaPullSeg;
+int bya_peer_pull(void* stream, const ByaPullSeg* segs, int n_segs, const void* const* peer_src, void* dst, int vec_bytes,
+                  int blocks_per_seg);
 
 /* ---------------------------------------------------------------- the step either side of the path
  * Classifier-free-guidance combine + CogVideoXDPMScheduler.step + the write of x_{t-1} into the next step's model

@@ -145,3 +145,67 @@ def test_cfg_slice_keeps_batch_axis_and_shared_inputs():
     assert isinstance(out, list) and isinstance(out[1], tuple) and out[0][1].shape == (1, 5)
     shared = torch.zeros(1, 10, 2)                      # forced routing logits are shared by both branches
     assert cfg_slice(shared, 1) is shared and cfg_slice(None, 0) is None
+
+
+@pytest.mark.parametrize("P,frames,hw,C", [(2, 3, 10, 2), (4, 13, 54, 2), (8, 13, 1350, 2), (8, 5, 37, 3), (4, 25, 96, 2)])
+def test_peer_pull_segment_tables_equal_the_nccl_path_layouts(P, frames, hw, C):
+    """The NVLink peer-memory exchanges (bya_b200/peer.py -> csrc/peer.cu) are described by strided-segment tables.  Each
+    table, applied by the host reference of the pull kernel to simulated per-rank buffers, must reproduce what the NCCL
+    path computes with all_to_all_single / all_gather + the permuting copies of bya_b200/sp.py — for every rank, incl. the
+    padded router shards of the real grid (1350 positions over 8 ranks) and a text / video boundary inside rank 0."""
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bya_b200  # noqa: F401
+    from bya_b200 import peer as pk
+    from bya_b200.sp import router_gather_positions, router_local_tokens, router_scatter_positions
+
+    rng = np.random.RandomState(0)
+    hwl = (hw + P - 1) // P
+    hw_pad = hwl * P
+    CF, R = C * frames, frames * hwl
+    M = C * R
+    hl = 8 // P if 8 % P == 0 else 1
+    Ws, Wo = 3 * hl * 64, hl * 64
+    # ---- router q|k|v gather: s_send[src][dest][M][Ws]
+    send = [rng.randint(0, 60000, size=(P, M, Ws)).astype(np.uint16) for _ in range(P)]
+    for r in range(P):
+        recv = torch.from_numpy(np.stack([send[s][r] for s in range(P)]).astype(np.int32))        # all_to_all_single
+        want = router_gather_positions(recv, CF, P, hwl).reshape(CF * hw_pad, Ws).numpy().astype(np.uint16)
+        got = np.zeros((CF * hw_pad, Ws), np.uint16)
+        pk.simulate_pull(pk.router_gather_segments(P, r, CF, hwl, M, Ws), send, got)
+        assert np.array_equal(got, want), r
+    # ---- router attention-output scatter: s_att[src][(cf)][hw_pad][Wo]
+    att = [rng.randint(0, 60000, size=(CF * hw_pad, Wo)).astype(np.uint16) for _ in range(P)]
+    o_send = [router_scatter_positions(torch.from_numpy(a.astype(np.int32)), CF, P, hwl).reshape(P, M, Wo) for a in att]
+    for r in range(P):
+        want = torch.stack([o_send[s][r] for s in range(P)]).numpy().astype(np.uint16)            # all_to_all_single
+        got = np.zeros((P, M, Wo), np.uint16)
+        pk.simulate_pull(pk.router_scatter_segments(P, r, CF, hwl, M, Wo), att, got)
+        assert np.array_equal(got, want), r
+    # ---- face queries of a rank's router positions: every rank owns rows [r*Rr, (r+1)*Rr) of [text; video]
+    T = 6
+    N = T + frames * hw
+    N += (-N) % P
+    T = N - frames * hw                      # keep N divisible by P (text rows absorb the remainder)
+    Rr, width = N // P, 16
+    allq = rng.randint(0, 60000, size=(N, width)).astype(np.uint16)
+    owned = [allq[r * Rr:(r + 1) * Rr].copy() for r in range(P)]
+    for r in range(P):
+        idx = router_local_tokens(frames, hw, P, r).numpy()
+        want = allq[T:][idx]                                                                          # all_gather + index_select
+        got = np.zeros((frames * hwl, width), np.uint16)
+        segs = pk.face_query_segments(P, r, frames, hw, T, Rr, width)
+        pk.simulate_pull(segs, owned, got)
+        assert np.array_equal(got, want), r
+        assert len(segs) <= 4 * frames + 2 * P
+    # ---- routing result: r_loc[src][frames*hwl][C] fp32 -> [frames*hw][C]
+    rloc = [rng.rand(frames * hwl, C).astype(np.float32) for _ in range(P)]
+    r_all = torch.from_numpy(np.stack(rloc)).view(P, frames, hwl, C)
+    want = r_all.permute(1, 0, 2, 3).reshape(frames, hw_pad, C)[:, :hw].reshape(frames * hw, C).numpy()
+    got = np.zeros((frames * hw, C), np.float32)
+    segs = pk.routing_gather_segments(P, frames, hw, C)
+    pk.simulate_pull(segs, rloc, got)
+    assert np.array_equal(got, want)
+    assert pk.vec_bytes_for(segs) == (8 if C == 2 else 4)
+    assert pk.vec_bytes_for(pk.router_gather_segments(P, 0, CF, hwl, M, Ws)) == 16
