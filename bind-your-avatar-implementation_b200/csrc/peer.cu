@@ -6,15 +6,18 @@
 //     destination rank's [q|k|v] column block straight into that rank's attention input (gemm_tcgen05.cu: peer_out), the
 //     attention epilogue stores each query row straight into the K-blocked A operand of its owner's out-projection
 //     (fa_tcgen05.cu: out_peers).  The exchange overlaps the math tile by tile; what remains is a barrier.
-//   * PULL: one kernel gathers strided segments from the peers' buffers into the local layout the consumer wants — the
-//     router's spatial-attention exchanges (the position gather / scatter permutations are folded into the segment
-//     strides), the face queries of a rank's router positions, the routing result.
+//   * COPY: one kernel moves strided segments between a local buffer and the peers' buffers in the layout the consumer
+//     wants — the router's spatial-attention exchanges (the position gather / scatter permutations are folded into the
+//     segment strides), the face queries of a rank's router positions, the routing result.  Pushed (posted writes) by
+//     default; a pull variant (remote reads) exists for comparison.
 // Ordering: a device-side epoch barrier (bya_peer_barrier): each rank release-stores its epoch into every peer's flag
 // array after its producer kernel has finished (stream order) and acquire-spins on its own flags.  Buffers need no
 // double buffering: between a consumer's read and the next overwrite of the same buffer there is always another barrier
 // of the same stream-ordered sequence.
 #include "common.cuh"
 #include "../../include/bya.h"
+
+#include <type_traits>
 
 namespace bya {
 
@@ -55,24 +58,44 @@ struct PullSeg {      // one strided 3-D block copied from a peer buffer into a 
 };
 static_assert(sizeof(PullSeg) == sizeof(ByaPullSeg), "ByaPullSeg layout");
 
-// grid (blocks per segment, n_segs).  src bases: peer_src[seg.peer]; VEC = bytes per access (16 / 8 / 4).
-template <int VEC>
-__global__ void __launch_bounds__(256) peer_pull_kernel(const PullSeg* __restrict__ segs, const char* const* __restrict__ peer_src,
-                                                        char* __restrict__ dst) {
+// grid (blocks per segment, n_segs).  PUSH: src = local + src_off, dst = peers[seg.peer] + dst_off (posted NVLink writes:
+// latency-tolerant, the default); PULL: src = peers[seg.peer] + src_off, dst = local + dst_off (remote reads need
+// ~2 MB in flight to cover the NVLink round trip: measured 16 GB/s with 4 096 threads of one load each).
+// VEC = bytes per access (16 / 8 / 4); four independent accesses in flight per thread.
+template <int VEC, bool PUSH>
+__global__ void __launch_bounds__(256) peer_copy_kernel(const PullSeg* __restrict__ segs, char* const* __restrict__ peers,
+                                                        char* __restrict__ local) {
+  using V = typename std::conditional<VEC == 16, uint4, typename std::conditional<VEC == 8, uint2, uint32_t>::type>::type;
   const PullSeg s = segs[blockIdx.y];
-  const char* src = peer_src[s.peer] + s.src_off;
-  char* d = dst + s.dst_off;
+  const char* src = (PUSH ? local : peers[s.peer]) + s.src_off;
+  char* d = (PUSH ? peers[s.peer] : local) + s.dst_off;
   const int per_row = s.row_bytes / VEC;
   const long long total = (long long)s.outer * s.rows * per_row;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto addr = [&](long long i, const char*& sp, char*& dp) {
     const int v = int(i % per_row);
     const long long rr = i / per_row;
     const int r = int(rr % s.rows), o = int(rr / s.rows);
-    const char* sp = src + o * s.src_outer_stride + r * s.src_row_stride + (long long)v * VEC;
-    char* dp = d + o * s.dst_outer_stride + r * s.dst_row_stride + (long long)v * VEC;
-    if (VEC == 16) *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
-    else if (VEC == 8) *reinterpret_cast<uint2*>(dp) = *reinterpret_cast<const uint2*>(sp);
-    else *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
+    sp = src + o * s.src_outer_stride + r * s.src_row_stride + (long long)v * VEC;
+    dp = d + o * s.dst_outer_stride + r * s.dst_row_stride + (long long)v * VEC;
+  };
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    const char* sp[4];
+    char* dp[4];
+    V val[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) addr(i + u * stride, sp[u], dp[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) val[u] = *reinterpret_cast<const V*>(sp[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) *reinterpret_cast<V*>(dp[u]) = val[u];
+  }
+  for (; i < total; i += stride) {
+    const char* sp;
+    char* dp;
+    addr(i, sp, dp);
+    *reinterpret_cast<V*>(dp) = *reinterpret_cast<const V*>(sp);
   }
 }
 
@@ -86,18 +109,23 @@ extern "C" int bya_peer_barrier(void* stream, int* counter, int* const* peer_fla
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }
 
-extern "C" int bya_peer_pull(void* stream, const ByaPullSeg* segs, int n_segs, const void* const* peer_src, void* dst, int vec_bytes,
-                             int blocks_per_seg) {
-  if (!segs || !peer_src || !dst || n_segs <= 0 || n_segs > 65535 || blocks_per_seg <= 0) return BYA_ERR_SHAPE;
+extern "C" int bya_peer_copy(void* stream, const ByaPullSeg* segs, int n_segs, void* const* peers, void* local, int push,
+                             int vec_bytes, int blocks_per_seg) {
+  if (!segs || !peers || !local || n_segs <= 0 || n_segs > 65535 || blocks_per_seg <= 0) return BYA_ERR_SHAPE;
   dim3 grid(blocks_per_seg, n_segs);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const PullSeg* sg = reinterpret_cast<const PullSeg*>(segs);
-  const char* const* ps = reinterpret_cast<const char* const*>(peer_src);
+  char* const* pp = reinterpret_cast<char* const*>(peers);
+  char* lc = static_cast<char*>(local);
+#define BYA_PEER_COPY(V)                                                        \
+  if (push) peer_copy_kernel<V, true><<<grid, 256, 0, s>>>(sg, pp, lc);         \
+  else peer_copy_kernel<V, false><<<grid, 256, 0, s>>>(sg, pp, lc)
   switch (vec_bytes) {
-    case 16: peer_pull_kernel<16><<<grid, 256, 0, s>>>(sg, ps, static_cast<char*>(dst)); break;
-    case 8: peer_pull_kernel<8><<<grid, 256, 0, s>>>(sg, ps, static_cast<char*>(dst)); break;
-    case 4: peer_pull_kernel<4><<<grid, 256, 0, s>>>(sg, ps, static_cast<char*>(dst)); break;
+    case 16: BYA_PEER_COPY(16); break;
+    case 8: BYA_PEER_COPY(8); break;
+    case 4: BYA_PEER_COPY(4); break;
     default: return BYA_ERR_ALIGN;
   }
+#undef BYA_PEER_COPY
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }

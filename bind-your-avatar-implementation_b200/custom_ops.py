@@ -243,6 +243,6 @@ def _peer_barrier(counter, flag_ptrs, my_rank, n_ranks):
     check(lib().bya_peer_barrier(_stream(), _ptr(counter), _ptr(flag_ptrs), my_rank, n_ranks), "peer_barrier")
 
 
-@_op("peer_pull(Tensor segs, int n_segs, Tensor src_ptrs, Tensor(a!) dst, int vec_bytes, int blocks_per_seg) -> ()")
-def _peer_pull(segs, n_segs, src_ptrs, dst, vec_bytes, blocks_per_seg):
-    check(lib().bya_peer_pull(_stream(), _ptr(segs), n_segs, _ptr(src_ptrs), _ptr(dst), vec_bytes, blocks_per_seg), "peer_pull")
+@_op("peer_copy(Tensor segs, int n_segs, Tensor peer_ptrs, Tensor(a!) local, int push, int vec_bytes, int blocks_per_seg) -> ()")
+def _peer_copy(segs, n_segs, peer_ptrs, local, push, vec_bytes, blocks_per_seg):
+    check(lib().bya_peer_copy(_stream(), _ptr(segs), n_segs, _ptr(peer_ptrs), _ptr(local), push, vec_bytes, blocks_per_seg), "peer_copy")

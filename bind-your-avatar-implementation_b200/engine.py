@@ -162,12 +162,12 @@ class RouterShard:
 
 
 def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: torch.Tensor, layer: int,
-                  chars: int, out: torch.Tensor, group, peer=None, q_ptrs=None, text_len: int = 0, rows_per_rank: int = 0) -> torch.Tensor:
+                  chars: int, out: torch.Tensor, group, peer=None, q_local=None, text_len: int = 0, rows_per_rank: int = 0) -> torch.Tensor:
     """`run_router` sharded over the sequence-parallel group: q_all [Nv,2048] (every rank holds all face queries; None with
-    the peer exchange, which pulls this rank's rows from their owners) -> out [Nv,C] fp32 on every rank.  Same kernels, same
-    per-row arithmetic as the single-GPU router.  Exchanges: NCCL all-to-all + permuting copies (peer=None), or one device
-    barrier + one strided pull from the peers' buffers each (`peer.py`; the position gather / scatter permutations are
-    folded into the segment strides)."""
+    the peer exchange, where every owner pushes the rows of `q_local` [rows_per_rank, 2048] the other ranks' routers need)
+    -> out [Nv,C] fp32 on every rank.  Same kernels, same per-row arithmetic as the single-GPU router.  Exchanges: NCCL
+    all-to-all + permuting copies (peer=None), or one strided push into the peers' buffers + one device barrier each
+    (`peer.py`; the position gather / scatter permutations are folded into the segment strides)."""
     import torch.distributed as dist
 
     from . import peer as pk
@@ -178,13 +178,22 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: 
     M = C * R                    # local router rows, ordered (character, frame, local position)
     CF = C * Fr
     Ws, Wo = 3 * hl * 64, hl * 64
-    qf = ws.get("rs_qsel", (R, 2048))
     if peer is None:
+        qf = ws.get("rs_qsel", (R, 2048))
         torch.index_select(q_all, 0, rs.idx, out=qf)
+        s_full = ws.get("rs_s_full", (CF * rs.hw_pad, Ws))   # [(c,f)][all positions (padded)][my heads]
+        o_recv = ws.get("rs_o_recv", (P, M, Wo))          # [src heads][local row] = K-blocked A of the out-projection
+        s_recv = ws.get("rs_s_recv", (P, M, Ws))          # [src][(c,f), src's positions][my heads]
+        o_send = ws.get("rs_o_send", (P, M, Wo))
     else:
-        peer.barrier()           # every owner's to_q GEMM has written its `face_q`
-        peer.pull(("face_q", Fr, rs.hw, text_len, rows_per_rank), lambda: pk.face_query_segments(
-            P, rs.rank, Fr, rs.hw, text_len, rows_per_rank, 2048), q_ptrs, qf, blocks_per_seg=4)
+        qf, _, qf_ptrs = peer.get("rs_qsel", (R, 2048))
+        s_full, _, s_full_ptrs = peer.get("rs_s_full", (CF * rs.hw_pad, Ws))
+        o_recv, _, o_recv_ptrs = peer.get("rs_o_recv", (P, M, Wo))
+        peer.push(("face_q", Fr, rs.hw, text_len, rows_per_rank), lambda d: pk.face_query_segments(
+            P, d, Fr, rs.hw, text_len, rows_per_rank, 2048), q_local, qf_ptrs)
+        peer.barrier()           # the queries of my router positions have landed
+    s_send = ws.get("rs_s_send", (P, M, Ws))              # [dest][local row][q|k|v heads of dest]
+    s_att = ws.get("rs_s_att", (CF * rs.hw_pad, Wo))
     rq = ws.get("rs_q", (R, 2048))
     ops.layernorm_modulate(qf, rq, eps=rp.eps, gamma=rp.nq_w, beta=rp.nq_b)
     rq2 = ws.get("rs_q2", (R, 2048))
@@ -198,16 +207,6 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: 
     xn = ws.get("rs_xn", (M, 512))
     qkv = ws.get("rs_qkv", (M, 1536))
     att = ws.get("rs_att", (M, 512))
-    s_full = ws.get("rs_s_full", (CF * rs.hw_pad, Ws))   # [(c,f)][all positions (padded)][my heads]
-    o_recv = ws.get("rs_o_recv", (P, M, Wo))          # [src heads][local row] = K-blocked A of the out-projection
-    if peer is None:
-        s_send = ws.get("rs_s_send", (P, M, Ws))          # [dest][local row][q|k|v heads of dest]
-        s_recv = ws.get("rs_s_recv", (P, M, Ws))          # [src][(c,f), src's positions][my heads]
-        s_att = ws.get("rs_s_att", (CF * rs.hw_pad, Wo))
-        o_send = ws.get("rs_o_send", (P, M, Wo))
-    else:
-        s_send, _, s_send_ptrs = peer.get("rs_s_send", (P, M, Ws))
-        s_att, _, s_att_ptrs = peer.get("rs_s_att", (CF * rs.hw_pad, Wo))
     for d, dsp in zip(rp.blocks, rs.blocks):
         # spatial: all H*W tokens of one (character, frame) — heads sharded, positions gathered
         ops.layernorm_modulate(x, xn, eps=d["n1"][2], gamma=d["n1"][0], beta=d["n1"][1])
@@ -216,18 +215,16 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: 
             dist.all_to_all_single(s_recv, s_send, group=group)
             s_full.view(CF, P, hwl, Ws).copy_(router_gather_positions(s_recv, CF, P, hwl))
         else:
+            peer.push(("rs_gather", CF, hwl, M, Ws), lambda r: pk.router_gather_segments(P, r, CF, hwl, M, Ws), s_send, s_full_ptrs)
             peer.barrier()
-            peer.pull(("rs_gather", CF, hwl, M, Ws), lambda: pk.router_gather_segments(P, rs.rank, CF, hwl, M, Ws),
-                      s_send_ptrs, s_full)
         ops.attention_d64(s_full[:, :Wo], s_full[:, Wo:2 * Wo], s_full[:, 2 * Wo:], s_att, CF, rs.hw, hl,
                           seq_stride=rs.hw_pad)
         if peer is None:
             o_send.view(P, CF, hwl, Wo).copy_(router_scatter_positions(s_att, CF, P, hwl))
             dist.all_to_all_single(o_recv, o_send, group=group)
         else:
+            peer.push(("rs_scatter", CF, hwl, M, Wo), lambda r: pk.router_scatter_segments(P, r, CF, hwl, M, Wo), s_att, o_recv_ptrs)
             peer.barrier()
-            peer.pull(("rs_scatter", CF, hwl, M, Wo), lambda: pk.router_scatter_segments(P, rs.rank, CF, hwl, M, Wo),
-                      s_att_ptrs, o_recv)
         ops.gemm(o_recv[0], d["s_o_w"], x, bias=d["s_o_b"], mode=ops.EPI_RESIDUAL, resid=x, a_kblock=Wo,
                  a_kblock_stride=M * Wo)
         # temporal: the F tokens at one (character, local position)
@@ -244,17 +241,16 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: 
         ops.layernorm_modulate(x, xn, eps=d["n4"][2], gamma=d["n4"][0], beta=d["n4"][1])
         ops.gemm(xn, d["m0_w"], att, bias=d["m0_b"], act=ops.ACT_GELU_ERF)
         ops.gemm(att, d["m2_w"], x, bias=d["m2_b"], mode=ops.EPI_RESIDUAL, resid=x)
+    r_loc = ws.get("rs_r_loc", (R, C), torch.float32)
+    ops.router_head(x, rp.head_w, rp.head_b, r_loc, R, C)
     if peer is None:
-        r_loc = ws.get("rs_r_loc", (R, C), torch.float32)
-        ops.router_head(x, rp.head_w, rp.head_b, r_loc, R, C)
         r_all = ws.get("rs_r_all", (P, Fr, hwl, C), torch.float32)
         dist.all_gather_into_tensor(r_all, r_loc, group=group)
         out.view(Fr, rs.hw, C).copy_(r_all.permute(1, 0, 2, 3).reshape(Fr, rs.hw_pad, C)[:, :rs.hw])
-    else:
-        r_loc, _, r_ptrs = peer.get("rs_r_loc", (R, C), torch.float32)
-        ops.router_head(x, rp.head_w, rp.head_b, r_loc, R, C)
+    else:   # `out` is the symmetric routing buffer: every rank writes its positions into everyone's copy
+        out_ptrs = peer.get("routing", tuple(out.shape), torch.float32)[2]
+        peer.push(("rs_routing", Fr, rs.hw, C), lambda r: pk.routing_gather_segments(P, Fr, rs.hw, C), r_loc, out_ptrs)
         peer.barrier()
-        peer.pull(("rs_routing", Fr, rs.hw, C), lambda: pk.routing_gather_segments(P, Fr, rs.hw, C), r_ptrs, out, blocks_per_seg=2)
     return out
 
 
@@ -624,7 +620,9 @@ class StepEngine:
         att = ws.get("att", (R, D))
         ffh = ws.get("ffh", (R, 4 * D))
         patches = ws.get("patches", (Nv, self.patch_k))
-        routing = ws.get("routing", (Nv, C), torch.float32)
+        pg0 = getattr(self, "peer", None) if P > 1 else None
+        # the routing result: with the peer exchange every rank's router pushes its positions into everyone's copy
+        routing = pg0.get("routing", (Nv, C), torch.float32)[0] if pg0 is not None else ws.get("routing", (Nv, C), torch.float32)
         aw = ws.get("aud_w", (max(Vl, 1), C), torch.float32)
         awsum = ws.get("aud_wsum", (max(Vl, 1),), torch.float32)
         pg = getattr(self, "peer", None) if P > 1 else None
@@ -679,23 +677,23 @@ class StepEngine:
                 elif pg is None:
                     ops.gemm(xn, L["w_qkv_sp"], qkv_send[0], bias=L["b_qkv_sp"], mode=ops.EPI_QKV, split_row=Tl,
                              ln_eps=L["qk_eps"], rope=(cos, sin), rope_row0=v0, nq=L["nq"], nk=L["nk"], qkv_block=3 * Dl,
-                             col_block=3 * Dl, col_block_stride=R * 3 * Dl, q_premul=qpm)
+                             col_block=3 * Dl, col_block_stride=R * 3 * Dl, q_premul=qpm, tag="qkv_gemm")
                     dist.all_to_all_single(qkv.view(P, R, 3 * Dl), qkv_send, group=self.sp_group)
                     ops.attention_d64(qkv[:, :Dl], qkv[:, Dl:2 * Dl], qkv[:, 2 * Dl:], o_send, 1, N, Hl_, tag="self_attention",
                                       score_bound_log2=sb)
                     dist.all_to_all_single(o_recv, o_send.view(P, R, Dl), group=self.sp_group)
                     ops.gemm(o_recv[0], L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g,
-                             split_row=Tl, a_kblock=Dl, a_kblock_stride=R * Dl)
+                             split_row=Tl, a_kblock=Dl, a_kblock_stride=R * Dl, tag="out_gemm")
                 else:
                     ops.gemm(xn, L["w_qkv_sp"], qkv_dst[0], bias=L["b_qkv_sp"], mode=ops.EPI_QKV, split_row=Tl,
                              ln_eps=L["qk_eps"], rope=(cos, sin), rope_row0=v0, nq=L["nq"], nk=L["nk"], qkv_block=3 * Dl,
-                             col_block=3 * Dl, q_premul=qpm, peer_out=qkv_dst)
+                             col_block=3 * Dl, q_premul=qpm, peer_out=qkv_dst, tag="qkv_gemm")
                     pg.barrier()      # every rank's q|k|v block has landed in my `qkv`
                     ops.attention_d64_scatter(qkv[:, :Dl], qkv[:, Dl:2 * Dl], qkv[:, 2 * Dl:], o_dst, R, N, Hl_,
                                               tag="self_attention", score_bound_log2=sb)
                     pg.barrier()      # every rank's heads have landed in my o_recv
                     ops.gemm(o_recv[0], L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g,
-                             split_row=Tl, a_kblock=Dl, a_kblock_stride=R * Dl)
+                             split_row=Tl, a_kblock=Dl, a_kblock_stride=R * Dl, tag="out_gemm")
                 ops.layernorm_modulate(x, xn, eps=L["ln2"][2], gamma=L["ln2"][0], beta=L["ln2"][1], mod_a=(esc2, esh2),
                                        mod_b=(sc2, sh2), split_row=Tl)
                 ops.gemm(xn, L["w_f1"], ffh, bias=L["b_f1"], act=ops.ACT_GELU_TANH)
@@ -708,11 +706,9 @@ class StepEngine:
                 if m.is_train_face and i % m.cross_attn_interval == 0 and ca < len(self.face):
                     Fc = self.face[ca]
                     dq = Fc["w_q"].shape[0]
-                    if pg is not None and use_router and getattr(m, "sp_shard_router", True):
-                        qpad, _, qpad_ptrs = pg.get("face_q", (R, dq))   # peers pull the rows of their router positions
-                    else:
-                        qpad, qpad_ptrs = ws.get("face_q", (R, dq)), None   # rows [Tl:] hold the local video queries
+                    qpad = ws.get("face_q", (R, dq))         # rows [Tl:] hold the local video queries
                     qf = qpad[Tl:]
+                    peer_router = pg is not None and use_router and getattr(m, "sp_shard_router", True)
                     if Vl:
                         xnv = xn[:Vl]
                         ops.layernorm_modulate(xv, xnv, eps=Fc["ln"][2], gamma=Fc["ln"][0], beta=Fc["ln"][1])
@@ -720,18 +716,18 @@ class StepEngine:
                     if use_router:
                         if P == 1:
                             q_all = qf
-                        elif qpad_ptrs is None:  # every rank needs the queries of its router positions in all frames: gather them
+                        elif not peer_router:  # every rank needs the queries of its router positions in all frames: gather them
                             qg = ws.get("face_q_all", (N, dq))
                             dist.all_gather_into_tensor(qg, qpad, group=self.sp_group)
                             q_all = qg[T:]
                         else:
-                            q_all = None         # pulled from the owners' `face_q` inside run_router_sp
+                            q_all = None         # every owner pushes the rows a rank's router needs (run_router_sp)
                         if P > 1 and getattr(m, "sp_shard_router", True):
                             rs = self._router_shard
                             if rs is None or (rs.frames, rs.hw, rs.P) != (Fr, hw, P):
                                 rs = self._router_shard = RouterShard(self.router, Fr, hw, P, rank, dev)
                             run_router_sp(self.router, rs, ws, q_all, pro["kmat"][b][ca], ca, C, routing, self.sp_group,
-                                          peer=pg, q_ptrs=qpad_ptrs, text_len=T, rows_per_rank=R)
+                                          peer=pg if peer_router else None, q_local=qpad, text_len=T, rows_per_rank=R)
                         else:
                             run_router(self.router, ws, q_all, pro["kmat"][b][ca], ca, C, Fr, hw, routing)
                         if tap and b == 0:

@@ -49,7 +49,7 @@ def _bf16_2d(t: torch.Tensor, name: str):
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=ACT_NONE, mode=EPI_STORE,
          resid=None, gate_a=None, gate_b=None, split_row=0, alpha=1.0, row_bias_scale=None,
          qkv_block=0, ln_eps=1e-6, rope=None, rope_row0=0, nq=None, nk=None, group_m=0, col_block=0,
-         col_block_stride=0, a_kblock=0, a_kblock_stride=0, q_premul=0.0, split_k=0, peer_out=None) -> torch.Tensor:
+         col_block_stride=0, a_kblock=0, a_kblock_stride=0, q_premul=0.0, split_k=0, peer_out=None, tag=None) -> torch.Tensor:
     """out = epilogue(a @ w.T); a [M,K], w [N,K], out [M,N] (row strides may exceed the width).
     With peer_out (a list of N/col_block [M, col_block] tensors, possibly views of OTHER ranks' memory): column block d is
     stored to peer_out[d]; pass out=peer_out[0].
@@ -78,9 +78,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
     if mode == EPI_QKV:
         rope_cos, rope_sin = rope
         (nq_w, nq_b), (nk_w, nk_b) = nq, nk
+    ev = _prof(tag)
     _bya.gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, float(alpha), row_bias_scale, qkv_block,
                    float(ln_eps), rope_cos, rope_sin, rope_row0, nq_w, nq_b, nk_w, nk_b, group_m, col_block, col_block_stride,
                    a_kblock, a_kblock_stride, float(q_premul), split_k, peer_out)
+    if ev is not None:
+        ev.record()
     LAUNCHES += 1
     return out
 
@@ -388,13 +391,21 @@ def peer_barrier(counter, flag_ptrs, my_rank, n_ranks):
     if counter.dtype != torch.int32 or flag_ptrs.dtype != torch.int64 or not counter.is_cuda or not flag_ptrs.is_cuda \
             or flag_ptrs.numel() < n_ranks:
         raise RuntimeError("bya_b200.peer_barrier: int32 counter and an int64 pointer table on the device")
+    ev = _prof("peer_barrier")
     _bya.peer_barrier(counter, flag_ptrs, my_rank, n_ranks)
+    if ev is not None:
+        ev.record()
     _count()
 
 
-def peer_pull(segs, n_segs, src_ptrs, dst, vec_bytes, blocks_per_seg=8):
-    if segs.dtype != torch.uint8 or segs.numel() != n_segs * 64 or not segs.is_cuda or src_ptrs.dtype != torch.int64 \
-            or not dst.is_cuda or not dst.is_contiguous():
-        raise RuntimeError("bya_b200.peer_pull: bad segment table / pointer table / destination")
-    _bya.peer_pull(segs, n_segs, src_ptrs, dst, vec_bytes, blocks_per_seg)
+def peer_copy(segs, n_segs, peer_ptrs, local, push, vec_bytes, blocks_per_seg=8):
+    """Strided segments between `local` and the peers' buffers (`peer_ptrs`: device table of base pointers); push: local ->
+    peers (posted writes), else peers -> local."""
+    if segs.dtype != torch.uint8 or segs.numel() != n_segs * 64 or not segs.is_cuda or peer_ptrs.dtype != torch.int64 \
+            or not local.is_cuda or not local.is_contiguous():
+        raise RuntimeError("bya_b200.peer_copy: bad segment table / pointer table / local buffer")
+    ev = _prof("peer_copy")
+    _bya.peer_copy(segs, n_segs, peer_ptrs, local, int(bool(push)), vec_bytes, blocks_per_seg)
+    if ev is not None:
+        ev.record()
     _count()

@@ -3,9 +3,9 @@
 the oracle is the single-GPU result.
 
 torch.distributed._symmetric_memory is used for what it is — plumbing: it allocates the exchange buffers and maps every
-rank's buffer into every other rank's address space.  The barrier, the pull kernel and the push epilogues are libbya.so.
+rank's buffer into every other rank's address space.  The barrier, the strided copy kernel and the push epilogues are libbya.so.
 
-`PeerGroup`      symmetric buffers by name (local tensor + one tensor view per peer), the epoch barrier, segment pulls
+`PeerGroup`      symmetric buffers by name (local tensor + one tensor view per peer), the epoch barrier, segment pushes
 `*_segments()`   pure functions building the strided-segment tables of each exchange (unit-tested on CPU against the
                  torch statements of the same permutations in `sp.py`)
 """
@@ -79,6 +79,32 @@ def routing_gather_segments(P: int, frames: int, hw: int, chars: int, esz: int =
     return np.array(segs, dtype=SEG_DTYPE)
 
 
+def push_table(make_pull, P: int, rank: int) -> np.ndarray:
+    """The PUSH table of `rank` from the pull tables of all ranks: whatever destination d would pull from `rank` is what
+    `rank` writes into d's buffer (same offsets and strides; `peer` becomes the destination)."""
+    out = []
+    for d in range(P):
+        t = make_pull(d)
+        t = t[t["peer"] == rank].copy()
+        t["peer"] = d
+        out.append(t)
+    return np.concatenate(out)
+
+
+def simulate_push(tables: List[np.ndarray], local_bufs: List[np.ndarray], dst_bufs: List[np.ndarray]):
+    """Host reference of `bya_peer_copy(push=1)` run by every rank (tests)."""
+    for r, segs in enumerate(tables):
+        src = local_bufs[r].view(np.uint8).reshape(-1)
+        for s in segs:
+            d = dst_bufs[int(s["peer"])].view(np.uint8).reshape(-1)
+            for o in range(int(s["outer"])):
+                for q in range(int(s["rows"])):
+                    a = int(s["src_off"] + o * s["src_outer_stride"] + q * s["src_row_stride"])
+                    b = int(s["dst_off"] + o * s["dst_outer_stride"] + q * s["dst_row_stride"])
+                    d[b:b + int(s["row_bytes"])] = src[a:a + int(s["row_bytes"])]
+    return dst_bufs
+
+
 def simulate_pull(segs: np.ndarray, peer_bufs: List[np.ndarray], dst: np.ndarray) -> np.ndarray:
     """Host reference of `bya_peer_pull` on byte arrays (tests)."""
     d = dst.view(np.uint8).reshape(-1)
@@ -115,10 +141,6 @@ class PeerGroup:
         self.rank, self.P = dist.get_rank(group), dist.get_world_size(group)
         if self.P > 8:
             raise RuntimeError("bya_b200.peer: at most 8 ranks (one NVSwitch domain)")
-        try:
-            symm_mem.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass
         self.bufs: Dict[str, tuple] = {}
         self.tables: Dict[str, tuple] = {}
         flags, peers, self.flag_ptrs = self._alloc((64,), torch.int32)
@@ -151,14 +173,17 @@ class PeerGroup:
         ops.peer_barrier(self.counter, self.flag_ptrs, self.rank, self.P)
         self.barriers += 1
 
-    def pull(self, key: str, make_segments, src_ptrs: torch.Tensor, dst: torch.Tensor, blocks_per_seg: int = 8):
-        """Runs the segment table `key` (built once by `make_segments()`) from the peers' buffers into `dst`."""
+    def push(self, key, make_pull, local_src: torch.Tensor, dst_ptrs: torch.Tensor, blocks: int = 592):
+        """Writes this rank's part of an exchange into the peers' (symmetric) destination buffers.  `make_pull(d)` is the
+        strided-segment table rank d would use to PULL the exchange; the push table is derived from it once per `key`.
+        `blocks` ~ CTAs in total (posted writes need far fewer bytes in flight than remote reads)."""
         from . import ops
 
         t = self.tables.get(key)
         if t is None:
-            segs = make_segments()
+            segs = push_table(make_pull, self.P, self.rank)
             dev = torch.from_numpy(segs.view(np.uint8).reshape(-1).copy()).to(self.device)
-            t = (dev, len(segs), vec_bytes_for(segs))
+            t = (dev, len(segs), vec_bytes_for(segs), max(1, min(64, blocks // max(len(segs), 1))))
             self.tables[key] = t
-        ops.peer_pull(t[0], t[1], src_ptrs, dst, t[2], blocks_per_seg)
+        if t[1]:
+            ops.peer_copy(t[0], t[1], dst_ptrs, local_src, True, t[2], t[3])

@@ -206,16 +206,17 @@ int bya_router_keys_scatter(void* stream, const void* k, long long ldk, void* ma
  * advanced by the kernel); peer_flags: device array of n_ranks pointers, peer_flags[r] = rank r's flag array [n_ranks]
  * (zero at start; peer-mapped).  Returns once every rank of the group has issued the same barrier. */
 int bya_peer_barrier(void* stream, int* counter, int* const* peer_flags, int my_rank, int n_ranks);
-/* bya_peer_pull: gathers n_segs strided 3-D blocks from peer buffers into a local buffer: for each segment, for o < outer,
- * r < rows: copy row_bytes bytes from peer_src[peer] + src_off + o*src_outer_stride + r*src_row_stride to
- * dst + dst_off + o*dst_outer_stride + r*dst_row_stride.  All offsets / strides / row_bytes multiples of vec_bytes
- * (16, 8 or 4).  segs and peer_src are device arrays. */
+/* bya_peer_copy: moves n_segs strided 3-D blocks between a local buffer and peer buffers.  push != 0: for each segment, for
+ * o < outer, r < rows: copy row_bytes bytes from local + src_off + o*src_outer_stride + r*src_row_stride to
+ * peers[peer] + dst_off + o*dst_outer_stride + r*dst_row_stride (posted NVLink writes); push == 0: the same with the roles
+ * swapped (source peers[peer], destination local: remote reads).  All offsets / strides / row_bytes multiples of vec_bytes
+ * (16, 8 or 4).  segs and peers are device arrays. */
 typedef struct ByaPullSeg {
   long long src_off, dst_off;
   long long src_outer_stride, dst_outer_stride, src_row_stride, dst_row_stride;
   int peer, outer, rows, row_bytes;
 } ByaPullSeg;
-int bya_peer_pull(void* stream, const ByaPullSeg* segs, int n_segs, const void* const* peer_src, void* dst, int vec_bytes,
+int bya_peer_copy(void* stream, const ByaPullSeg* segs, int n_segs, void* const* peers, void* local, int push, int vec_bytes,
                   int blocks_per_seg);
 
 /* ---------------------------------------------------------------- the step either side of the path

@@ -209,3 +209,17 @@ def test_peer_pull_segment_tables_equal_the_nccl_path_layouts(P, frames, hw, C):
     assert np.array_equal(got, want)
     assert pk.vec_bytes_for(segs) == (8 if C == 2 else 4)
     assert pk.vec_bytes_for(pk.router_gather_segments(P, 0, CF, hwl, M, Ws)) == 16
+    # ---- the PUSH tables the kernels actually run (derived from the pull tables): every rank writes its part into the
+    # destination ranks' buffers; the union over ranks must give every rank exactly what its pull would have fetched
+    def check_push(make_pull, local_bufs, shape, dtype):
+        tables = [pk.push_table(make_pull, P, r) for r in range(P)]
+        dsts = [np.zeros(shape, dtype) for _ in range(P)]
+        pk.simulate_push(tables, local_bufs, dsts)
+        for r in range(P):
+            want = pk.simulate_pull(make_pull(r), local_bufs, np.zeros(shape, dtype))
+            assert np.array_equal(dsts[r], want), r
+
+    check_push(lambda r: pk.router_gather_segments(P, r, CF, hwl, M, Ws), send, (CF * hw_pad, Ws), np.uint16)
+    check_push(lambda r: pk.router_scatter_segments(P, r, CF, hwl, M, Wo), att, (P, M, Wo), np.uint16)
+    check_push(lambda r: pk.face_query_segments(P, r, frames, hw, T, Rr, width), owned, (frames * hwl, width), np.uint16)
+    check_push(lambda r: pk.routing_gather_segments(P, frames, hw, C), rloc, (frames * hw, C), np.float32)
