@@ -329,6 +329,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--no-sp-check", action="store_true")
+    ap.add_argument("--no-loop", action="store_true", help="skip the device-resident denoising loop (denoise_loop key)")
     ap.add_argument("--cfg-parallel", action="store_true",
                     help="N>1, --config c3: the two CFG branches on the two halves of the GPUs (each half sequence-parallel)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
@@ -475,7 +476,7 @@ def main():
     # ---- the device-resident denoising loop (guidance + DPM solver step fused, one graph replay per
     # step, prologue once per generation as in a real run) — reported beside the headline, not instead of it
     loop_info = None
-    if world == 1 and model.use_cuda_graph:
+    if model.use_cuda_graph and not args.no_loop:
         from bya_b200.denoise import DenoiseLoop
         from bya_b200.scheduler import CogVideoXDPMScheduler
 
@@ -489,6 +490,10 @@ def main():
                  generator=torch.Generator(device=dev).manual_seed(0))
         torch.cuda.synchronize()
         loop_ms = loop.loop_events[0].elapsed_time(loop.loop_events[1]) / n_loop
+        if world > 1:
+            tl = torch.tensor([loop_ms], device=dev)
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            loop_ms = float(tl.item())
         loop_info = {"ms_per_step": loop_ms, "steps_per_s": 1e3 / loop_ms, "steps": n_loop,
                      "gpu_launches_per_step": (ops.LAUNCHES - l1) // n_loop,
                      "what": "DenoiseLoop: [select timestep, transformer step, CFG combine + CogVideoXDPMScheduler.step + "

@@ -566,6 +566,16 @@ extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W
     // measured (gpurun_out/gemm_pair.log): pairs win 9-15 % on the K >= 3072 DiT shapes and lose 12 % on the K = 512
     // router GEMMs, whose 8 k-blocks are over before the deeper pipeline and the cluster launch pay off
     const bool pair = a.mode != GEMM_EPI_SPLITK_F32 && (force ? force == 2 : (a.M > 256 && a.K >= 1024));
+    if (pair && !a.col_block && a.mode != GEMM_EPI_QKV) {
+      // Wave quantisation with few tiles (the per-rank M of sequence parallelism: 2 222 rows x 3 072 columns = 108
+      // pair tiles = 1.46 waves of 74 pairs): 256 x 128 pair tiles halve the tail at ~8 % lower per-tile efficiency
+      // (each CTA stages 64 weight rows per k-block: the operand traffic per MMA of the single-CTA 128 x 256 tile).
+      const long long pairs = bya_host::num_sms() / 2;
+      const long long t256 = (long long)((a.M + 255) / 256) * (a.N / 256);
+      const double c256 = double((t256 + pairs - 1) / pairs);
+      const double c128 = double((2 * t256 + pairs - 1) / pairs) * 0.5 / 0.92;
+      if (c128 < 0.97 * c256 && std::getenv("BYA_GEMM_NO_PAIR128") == nullptr) return launch_gemm<128, 2>(a, A, lda, W, ldw, s);
+    }
     return pair ? launch_gemm<256, 2>(a, A, lda, W, ldw, s) : launch_gemm<256, 1>(a, A, lda, W, ldw, s);
   }
   if (a.N % 128 == 0) return launch_gemm<128, 1>(a, A, lda, W, ldw, s);

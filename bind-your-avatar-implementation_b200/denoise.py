@@ -77,8 +77,14 @@ class DenoiseLoop:
             id_cond, id_vit_hidden, audio_embeds, af_matrix = prepare_cfg_conditions(
                 id_cond, id_vit_hidden, audio_embeds, af_matrix, self.do_cfg, self.zero2cond)
         m, sch = self.transformer, self.scheduler
-        if getattr(m, "_sp_group", None) is not None or getattr(m, "_cfg", None) is not None:
-            raise NotImplementedError("bya_b200.DenoiseLoop: single-GPU loop; multi-GPU runs call the transformer per step")
+        # Multi-GPU (bya_b200.sp.enable): every rank runs the same loop on the same inputs and the same noise draws (seed the
+        # generators identically).  Sequence parallel: the step returns the full prediction on every rank, the solver step
+        # is replicated.  Batch-parallel CFG: this rank computes ONE guidance branch of the static model input and the two
+        # predictions are exchanged (`sp.cfg_gather`) before the fused guidance + solver kernel.
+        cfgp = getattr(m, "_cfg", None)
+        multi = getattr(m, "_sp_group", None) is not None or cfgp is not None
+        if cfgp is not None and not self.do_cfg:
+            raise ValueError("bya_b200.DenoiseLoop: cfg_parallel needs classifier-free guidance (two branches)")
         dev = m.device
         bf = torch.bfloat16
         B = 2 if self.do_cfg else 1
@@ -113,12 +119,20 @@ class DenoiseLoop:
                   audio_embeds=None if aud is None else aud.to(dev), af_matrix=None if af_matrix is None else af_matrix.to(dev),
                   routing_logits_forcing=None if use_router else routing_logits_forcing.to(dev),
                   per_frame_forcing=per_frame_forcing, cache_prologue=False)
+        if cfgp is not None:   # this rank's guidance branch: views into the static buffers (x is rewritten every step)
+            from .sp import cfg_gather, cfg_slice
+
+            br = cfgp["branch"]
+            for k in ("hidden_states", "encoder_hidden_states", "timestep", "id_cond", "id_vit_hidden", "audio_embeds", "af_matrix"):
+                kw[k] = cfg_slice(kw[k], br)
         kw["_pro"] = eng.prologue(kw["id_cond"], kw["id_vit_hidden"], kw["audio_embeds"], F, use_router)
         pt = _PRED[sch.config.prediction_type]
 
         def one_step():
             ops.denoise_select_step(st["ts"], st["t"], st["counter"], st["idx"])
             out = eng.step(**kw)
+            if cfgp is not None:
+                out = cfg_gather(out, cfgp)
             ops.cfg_dpm_step(out, st["lat"], st["lat"], st["pred"], st["pred"], st["noise"], st["coef"],
                              prediction_type=pt, step_index=st["idx"], model_input=st["x"])
 
@@ -131,7 +145,8 @@ class DenoiseLoop:
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             l0 = ops.LAUNCHES
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog thread of a multi-GPU run may query events while we capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if multi else "global"):
                 one_step()
             per_replay = ops.LAUNCHES - l0
             ops.LAUNCHES = l0

@@ -111,4 +111,12 @@ if which in ("all", "big"):
     bench(17776, 3072, 12288)
     bench(35100, 512, 512)
     bench(8192, 8192, 8192)
+if which in ("all", "sp"):   # per-rank shapes of 8- and 4-way sequence parallelism (wave-quantised: 256 x 128 pair tiles)
+    ok &= test_store(2222, 3072, 12288)
+    ok &= test_resid(2222, 3072, 3072, 226)
+    for M in (2222, 4444):
+        bench(M, 3072, 12288)
+        bench(M, 3072, 3072)
+        bench(M, 9216, 3072)
+        bench(M, 12288, 3072, act=1)
 print("ALL OK" if ok else "SOME FAILED")
