@@ -87,7 +87,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int splits = p.split_k > 1 ? p.split_k : 1;   // GEMM_EPI_SPLITK_F32: k-ranges run as independent tiles
   const int num_tiles = num_m * num_n * splits;
   const int num_kb = p.K / BK;
-  constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // power of 2
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -566,15 +566,16 @@ extern "C" int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W
     // measured (gpurun_out/gemm_pair.log): pairs win 9-15 % on the K >= 3072 DiT shapes and lose 12 % on the K = 512
     // router GEMMs, whose 8 k-blocks are over before the deeper pipeline and the cluster launch pay off
     const bool pair = a.mode != GEMM_EPI_SPLITK_F32 && (force ? force == 2 : (a.M > 256 && a.K >= 1024));
-    if (pair && !a.col_block && a.mode != GEMM_EPI_QKV) {
-      // Wave quantisation with few tiles (the per-rank M of sequence parallelism: 2 222 rows x 3 072 columns = 108
-      // pair tiles = 1.46 waves of 74 pairs): 256 x 128 pair tiles halve the tail at ~8 % lower per-tile efficiency
-      // (each CTA stages 64 weight rows per k-block: the operand traffic per MMA of the single-CTA 128 x 256 tile).
+    if (pair && !a.col_block && a.mode != GEMM_EPI_QKV && a.N % 192 == 0) {
+      // Wave quantisation with few tiles (the per-rank M of 8-way sequence parallelism: 2 222 rows x 3 072 columns = 108
+      // pair tiles = 1.46 waves of 74 pairs, i.e. 27 % of the second wave idle): 256 x 192 pair tiles make it 144 tiles
+      // = 1.95 waves of 3/4-size tiles.  (256 x 128 pair tiles were measured SLOWER: 0.156 vs 0.134 ms at
+      // 2222 x 3072 x 12288 — per-tile efficiency drops faster than the tail shrinks.)
       const long long pairs = bya_host::num_sms() / 2;
-      const long long t256 = (long long)((a.M + 255) / 256) * (a.N / 256);
-      const double c256 = double((t256 + pairs - 1) / pairs);
-      const double c128 = double((2 * t256 + pairs - 1) / pairs) * 0.5 / 0.92;
-      if (c128 < 0.97 * c256 && std::getenv("BYA_GEMM_NO_PAIR128") == nullptr) return launch_gemm<128, 2>(a, A, lda, W, ldw, s);
+      const long long mt = (a.M + 255) / 256;
+      const double c256 = double((mt * (a.N / 256) + pairs - 1) / pairs);
+      const double c192 = double((mt * (a.N / 192) + pairs - 1) / pairs) * 0.75 / 0.96;
+      if (c192 < 0.97 * c256 && std::getenv("BYA_GEMM_NO_PAIR192") == nullptr) return launch_gemm<192, 2>(a, A, lda, W, ldw, s);
     }
     return pair ? launch_gemm<256, 2>(a, A, lda, W, ldw, s) : launch_gemm<256, 1>(a, A, lda, W, ldw, s);
   }
