@@ -196,8 +196,9 @@ def audio_context(P: ProloguePack, ws, audio, frames: int):
     for r in range(R):
         ops.copy2d(torch.as_strided(a2[r], (Lw, win * per), (st * per, 1)), x1[r * Lw:(r + 1) * Lw])
     inter = A["w1"].shape[0]
-    n_tiles = ((R * Lw + 127) // 128) * (inter // 256 if inter % 256 == 0 else inter // 64)
-    sk = _split_k(n_tiles, x1.shape[1] // 64)
+    # (k-splits chosen from the weight shape only: the summation order, hence the result, must not depend on how many
+    # characters / CFG branches share the batch)
+    sk = _split_k(inter // 256 if inter % 256 == 0 else inter // 64, x1.shape[1] // 64)
     acc1 = ws.get("aud_acc1", (sk, R * Lw, inter), torch.float32)
     ops.gemm(x1, A["w1"], acc1, mode=ops.EPI_SPLITK_F32, split_k=sk)
     h1 = ws.get("aud_h1", (R * Lw, inter))
@@ -219,8 +220,7 @@ def audio_context(P: ProloguePack, ws, audio, frames: int):
         pin = ws.get(f"aud_pairs{level}", (R * pairs, 2 * CD))
         xv = x.view(R, L * CD)
         ops.copy2d(xv[:, keep * CD:], pin.view(R, pairs * 2 * CD))   # frames (keep + 2i, keep + 2i + 1) side by side
-        n_tiles = ((R * pairs + 127) // 128) * (CD // 256)
-        sk = _split_k(n_tiles, 2 * CD // 64)
+        sk = _split_k(CD // 256, 2 * CD // 64)
         acc = ws.get(f"aud_acc_c{level}", (sk, R * pairs, CD), torch.float32)
         ops.gemm(pin, A["wc"], acc, mode=ops.EPI_SPLITK_F32, split_k=sk)
         xn = ws.get(f"aud_x{level}", (R * Ln, CD))
