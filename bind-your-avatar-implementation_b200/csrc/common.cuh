@@ -113,6 +113,21 @@ BYA_DEVICE void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0,
 BYA_DEVICE void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// explicit shared-space accesses (a pointer cast from the dynamic shared buffer is GENERIC to ptxas: LD.E / ST.E, which go
+// through the long scoreboard like global loads)
+BYA_DEVICE float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+BYA_DEVICE float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+BYA_DEVICE void sts_f2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
 BYA_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 BYA_DEVICE void tma_store_wait_read() {
@@ -269,6 +284,11 @@ BYA_DEVICE uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
 }
 BYA_DEVICE void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Same without the cluster-scope release fence (no MEMBAR / ERRBAR in front of the arrive): for arrivals that only hand
+// back TENSOR memory — ordered by tcgen05.fence::before_thread_sync — and publish no ordinary memory writes.
+BYA_DEVICE void mbar_arrive_remote_nofence(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are credited to a barrier that may live in the PEER CTA of the pair
 BYA_DEVICE void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1,

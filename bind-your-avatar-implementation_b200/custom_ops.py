@@ -15,7 +15,7 @@ from typing import Optional
 
 import torch
 
-from .lib import ByaDpmStepArgs, ByaGemmArgs, check, lib
+from .lib import ByaChainArgs, ByaDpmStepArgs, ByaGemmArgs, check, lib
 
 _LIB = torch.library.Library("bya", "DEF")
 OP_NAMES = []
@@ -68,6 +68,22 @@ def _gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, alp
         for d, t in enumerate(peer_out):
             g.peer_out[d] = t.data_ptr()
     check(lib().bya_gemm_bf16(_stream(), _ptr(a), a.stride(0), _ptr(w), w.stride(0), ctypes.byref(g)), "gemm")
+
+
+@_op("gemm_ln_gemm_bf16(Tensor a1, Tensor w1, Tensor? b1, Tensor resid, Tensor(a!) x_out, int store_x, Tensor w2f, "
+     "Tensor csum, Tensor b2, float ln_eps, int act, Tensor(b!) out2, int n_split, int col_block, int col_block_stride, "
+     "int a_kblock, int a_kblock_stride) -> ()")
+def _gemm_ln_gemm_bf16(a1, w1, b1, resid, x_out, store_x, w2f, csum, b2, ln_eps, act, out2, n_split, col_block,
+                       col_block_stride, a_kblock, a_kblock_stride):
+    g = ByaChainArgs()
+    g.M, g.N2, g.act, g.n_split = a1.shape[0], w2f.shape[0], act, n_split
+    g.b1, g.resid, g.ldr = _ptr(b1), _ptr(resid), resid.stride(0)
+    g.x_out, g.ldx, g.store_x, g.ln_eps = _ptr(x_out), x_out.stride(0), store_x, ln_eps
+    g.csum, g.b2, g.out2, g.ldc = _ptr(csum), _ptr(b2), _ptr(out2), out2.stride(-2)
+    g.col_block, g.col_block_stride = col_block, col_block_stride
+    g.a_kblock, g.a_kblock_stride = a_kblock, a_kblock_stride
+    check(lib().bya_gemm_ln_gemm_bf16(_stream(), _ptr(a1), a1.stride(0), _ptr(w1), w1.stride(0), _ptr(w2f), w2f.stride(0),
+                                      ctypes.byref(g)), "gemm_ln_gemm")
 
 
 @_op("attention_d64(Tensor q, Tensor k, Tensor v, Tensor(a!) out, int batch, int seq, int seq_stride, int heads, "

@@ -61,6 +61,11 @@ class RouterPack:
                 d[k] = (_bf(n.weight), _bf(n.bias), n.eps)
             d["m0_w"], d["m0_b"] = _bf(blk.mlp[0].weight), _bf(blk.mlp[0].bias)
             d["m2_w"], d["m2_b"] = _bf(blk.mlp[2].weight), _bf(blk.mlp[2].bias)
+            # LayerNorm folded into the linear that follows it, for the fused links (`ops.gemm_ln_gemm`):
+            # f_s = norm1 -> spatial qkv, f_t = norm2 -> temporal qkv, f_i = norm3 -> multi-ID qkv, f_m = norm4 -> mlp[0]
+            for k, n, w, b in (("f_s", "n1", "s_qkv_w", "s_qkv_b"), ("f_t", "n2", "t_qkv_w", "t_qkv_b"),
+                               ("f_i", "n3", "i_qkv_w", "i_qkv_b"), ("f_m", "n4", "m0_w", "m0_b")):
+                d[k] = ops.fold_layernorm(d[w], d[b], d[n][0], d[n][1])
             self.blocks.append(d)
         self.head_w, self.head_b = _bf(router.final_proj[0].weight.reshape(-1)), _bf(router.final_proj[0].bias)
 
@@ -98,7 +103,7 @@ def _tree_values(x):
 
 
 def run_router(rp: RouterPack, ws: _Workspace, qf: torch.Tensor, kmat: torch.Tensor, layer: int, chars: int, frames: int,
-               hw: int, out: torch.Tensor) -> torch.Tensor:
+               hw: int, out: torch.Tensor, fused: bool = True) -> torch.Tensor:
     """qf [Nv,2048] (natural head-major face queries) , kmat [C*512,2048] -> out [Nv,C] fp32 soft routing.
     MultiIPRouter.forward (router.py:364-411) + SpatialTemporalAttentionBlock.forward (:468-493)."""
     Nv = qf.shape[0]
@@ -116,6 +121,26 @@ def run_router(rp: RouterPack, ws: _Workspace, qf: torch.Tensor, kmat: torch.Ten
     xn = ws.get("r_xn", (M, 512))
     qkv = ws.get("r_qkv", (M, 1536))
     att = ws.get("r_att", (M, 512))
+    if fused:
+        # every `x += proj(...)` + next LayerNorm + next projection is one kernel (`bya_gemm_ln_gemm_bf16`)
+        nb = len(rp.blocks)
+        for bi, d in enumerate(rp.blocks):
+            if bi == 0:
+                ops.layernorm_modulate(x, xn, eps=d["n1"][2], gamma=d["n1"][0], beta=d["n1"][1])
+                ops.gemm(xn, d["s_qkv_w"], qkv, bias=d["s_qkv_b"])
+            ops.attention_d64(qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:], att, C * frames, hw, 8)
+            ops.gemm_ln_gemm(att, d["s_o_w"], d["s_o_b"], x, x, *d["f_t"], qkv, ln_eps=d["n2"][2])
+            ops.small_attention(qkv, att, C * hw, frames, 8, hw, Nv, hw)
+            ops.gemm_ln_gemm(att, d["t_o_w"], d["t_o_b"], x, x, *d["f_i"], qkv, ln_eps=d["n3"][2])
+            ops.small_attention(qkv, att, Nv, C, 8, Nv, 0, Nv)
+            ops.gemm_ln_gemm(att, d["i_o_w"], d["i_o_b"], x, x, *d["f_m"], xn, ln_eps=d["n4"][2], act=ops.ACT_GELU_ERF)
+            if bi + 1 < nb:
+                dn = rp.blocks[bi + 1]
+                ops.gemm_ln_gemm(xn, d["m2_w"], d["m2_b"], x, x, *dn["f_s"], qkv, ln_eps=dn["n1"][2])
+            else:
+                ops.gemm(xn, d["m2_w"], x, bias=d["m2_b"], mode=ops.EPI_RESIDUAL, resid=x)
+        ops.router_head(x, rp.head_w, rp.head_b, out, Nv, C)
+        return out
     for d in rp.blocks:
         # spatial: all H*W tokens of one (character, frame)
         ops.layernorm_modulate(x, xn, eps=d["n1"][2], gamma=d["n1"][0], beta=d["n1"][1])
@@ -158,11 +183,13 @@ class RouterShard:
         self.idx = router_local_tokens(frames, hw, world, rank, device)    # [F*hwl] global token of each local row
         self.pos = rp.pos.index_select(0, self.idx).contiguous()
         self.blocks = [dict(w=qkv_rows_by_destination(d["s_qkv_w"], 512, world),
-                            b=qkv_rows_by_destination(d["s_qkv_b"], 512, world)) for d in rp.blocks]
+                            b=qkv_rows_by_destination(d["s_qkv_b"], 512, world),
+                            f_s=tuple(qkv_rows_by_destination(t, 512, world) for t in d["f_s"])) for d in rp.blocks]
 
 
 def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: torch.Tensor, layer: int,
-                  chars: int, out: torch.Tensor, group, peer=None, q_local=None, text_len: int = 0, rows_per_rank: int = 0) -> torch.Tensor:
+                  chars: int, out: torch.Tensor, group, peer=None, q_local=None, text_len: int = 0, rows_per_rank: int = 0,
+                  fused: bool = True) -> torch.Tensor:
     """`run_router` sharded over the sequence-parallel group: q_all [Nv,2048] (every rank holds all face queries; None with
     the peer exchange, where every owner pushes the rows of `q_local` [rows_per_rank, 2048] the other ranks' routers need)
     -> out [Nv,C] fp32 on every rank.  Same kernels, same per-row arithmetic as the single-GPU router.  Exchanges: NCCL
@@ -207,10 +234,13 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: 
     xn = ws.get("rs_xn", (M, 512))
     qkv = ws.get("rs_qkv", (M, 1536))
     att = ws.get("rs_att", (M, 512))
-    for d, dsp in zip(rp.blocks, rs.blocks):
+    x2 = ws.get("rs_x2", (M, 512)) if fused else None     # fused links with column slices write X out of place
+    nb = len(rp.blocks)
+    for bi, (d, dsp) in enumerate(zip(rp.blocks, rs.blocks)):
         # spatial: all H*W tokens of one (character, frame) — heads sharded, positions gathered
-        ops.layernorm_modulate(x, xn, eps=d["n1"][2], gamma=d["n1"][0], beta=d["n1"][1])
-        ops.gemm(xn, dsp["w"], s_send[0], bias=dsp["b"], col_block=Ws, col_block_stride=M * Ws)
+        if not fused or bi == 0:
+            ops.layernorm_modulate(x, xn, eps=d["n1"][2], gamma=d["n1"][0], beta=d["n1"][1])
+            ops.gemm(xn, dsp["w"], s_send[0], bias=dsp["b"], col_block=Ws, col_block_stride=M * Ws)
         if peer is None:
             dist.all_to_all_single(s_recv, s_send, group=group)
             s_full.view(CF, P, hwl, Ws).copy_(router_gather_positions(s_recv, CF, P, hwl))
@@ -225,6 +255,27 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: 
         else:
             peer.push(("rs_scatter", CF, hwl, M, Wo), lambda r: pk.router_scatter_segments(P, r, CF, hwl, M, Wo), s_att, o_recv_ptrs)
             peer.barrier()
+        if fused:
+            # `x += proj(...)` + next LayerNorm + next projection as one kernel each (`bya_gemm_ln_gemm_bf16`)
+            ops.gemm_ln_gemm(o_recv[0], d["s_o_w"], d["s_o_b"], x, x2, *d["f_t"], qkv, ln_eps=d["n2"][2],
+                             n_split=ops.chain_n_split(M, 1536), a_kblock=Wo, a_kblock_stride=M * Wo)
+            x, x2 = x2, x
+            ops.small_attention(qkv, att, C * hwl, Fr, 8, hwl, R, hwl)
+            ops.gemm_ln_gemm(att, d["t_o_w"], d["t_o_b"], x, x2, *d["f_i"], qkv, ln_eps=d["n3"][2],
+                             n_split=ops.chain_n_split(M, 1536))
+            x, x2 = x2, x
+            ops.small_attention(qkv, att, R, C, 8, R, 0, R)
+            ops.gemm_ln_gemm(att, d["i_o_w"], d["i_o_b"], x, x2, *d["f_m"], xn, ln_eps=d["n4"][2], act=ops.ACT_GELU_ERF,
+                             n_split=ops.chain_n_split(M, 512))
+            x, x2 = x2, x
+            if bi + 1 < nb:
+                dn, dspn = rp.blocks[bi + 1], rs.blocks[bi + 1]
+                ops.gemm_ln_gemm(xn, d["m2_w"], d["m2_b"], x, x2, *dspn["f_s"], s_send[0], ln_eps=dn["n1"][2],
+                                 n_split=ops.chain_n_split(M, 1536), col_block=Ws, col_block_stride=M * Ws)
+                x, x2 = x2, x
+            else:
+                ops.gemm(xn, d["m2_w"], x, bias=d["m2_b"], mode=ops.EPI_RESIDUAL, resid=x)
+            continue
         ops.gemm(o_recv[0], d["s_o_w"], x, bias=d["s_o_b"], mode=ops.EPI_RESIDUAL, resid=x, a_kblock=Wo,
                  a_kblock_stride=M * Wo)
         # temporal: the F tokens at one (character, local position)
@@ -530,6 +581,7 @@ class StepEngine:
         C = len(id_cond)
         use_router = routing_logits_forcing is None
         has_audio = audio_embeds is not None and len(self.audio) > 0
+        fused_links = bool(getattr(m, "fused_router_links", True))   # router block chain on bya_gemm_ln_gemm_bf16
         # taps: a dict (filled with fp32 CPU copies) or a callable(name, device tensor) — single-GPU debugging aid
         tap = taps if callable(taps) else (
             (lambda k, v: taps.__setitem__(k, v.detach().float().cpu().clone())) if taps is not None else None)
@@ -727,9 +779,10 @@ class StepEngine:
                             if rs is None or (rs.frames, rs.hw, rs.P) != (Fr, hw, P):
                                 rs = self._router_shard = RouterShard(self.router, Fr, hw, P, rank, dev)
                             run_router_sp(self.router, rs, ws, q_all, pro["kmat"][b][ca], ca, C, routing, self.sp_group,
-                                          peer=pg if peer_router else None, q_local=qpad, text_len=T, rows_per_rank=R)
+                                          peer=pg if peer_router else None, q_local=qpad, text_len=T, rows_per_rank=R,
+                                          fused=fused_links)
                         else:
-                            run_router(self.router, ws, q_all, pro["kmat"][b][ca], ca, C, Fr, hw, routing)
+                            run_router(self.router, ws, q_all, pro["kmat"][b][ca], ca, C, Fr, hw, routing, fused=fused_links)
                         if tap and b == 0:
                             tap(f"ca{ca}.router", routing)
                     if Vl:

@@ -28,6 +28,17 @@ class ByaGemmArgs(ctypes.Structure):
     ]
 
 
+class ByaChainArgs(ctypes.Structure):
+    _fields_ = [
+        ("M", ctypes.c_int), ("N2", ctypes.c_int), ("act", ctypes.c_int), ("n_split", ctypes.c_int),
+        ("b1", ctypes.c_void_p), ("resid", ctypes.c_void_p), ("ldr", ctypes.c_int),
+        ("x_out", ctypes.c_void_p), ("ldx", ctypes.c_int), ("store_x", ctypes.c_int), ("ln_eps", ctypes.c_float),
+        ("csum", ctypes.c_void_p), ("b2", ctypes.c_void_p), ("out2", ctypes.c_void_p), ("ldc", ctypes.c_int),
+        ("col_block", ctypes.c_int), ("col_block_stride", ctypes.c_longlong),
+        ("a_kblock", ctypes.c_int), ("a_kblock_stride", ctypes.c_longlong),
+    ]
+
+
 class ByaDpmStepArgs(ctypes.Structure):
     _fields_ = [
         ("frames", ctypes.c_int), ("channels", ctypes.c_int), ("hw", ctypes.c_int),

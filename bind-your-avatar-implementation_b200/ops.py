@@ -88,6 +88,57 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
     return out
 
 
+def fold_layernorm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm affine folded into the following linear: LN(x)·W^T + b = rstd * (x·W'^T - mean * csum) + b' with
+    W' = bf16(W diag(gamma)), csum = rowsum(W'), b' = b + W·beta (`bya_gemm_ln_gemm_bf16`, include/bya.h)."""
+    wf = (w.float() * gamma.float()[None, :]).to(torch.bfloat16).contiguous()
+    csum = wf.float().sum(1).contiguous()
+    b2 = w.float() @ beta.float()
+    if bias is not None:
+        b2 = b2 + bias.float()
+    return wf, csum, b2.contiguous()
+
+
+def chain_n_split(rows: int, n2: int) -> int:
+    """Column slices for `gemm_ln_gemm`: with few rows one CTA pair per 256-row tile leaves most SMs idle, so the N2
+    columns are cut into slices that run on different pairs (the small first GEMM is recomputed per slice)."""
+    pairs = 74
+    tiles = (rows + 255) // 256
+    best = 1
+    for s in (2, 3, 4, 6, 12):
+        if (n2 // 128) % s == 0 and tiles * s <= pairs:
+            best = s
+    return best
+
+
+def gemm_ln_gemm(a1: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], resid: torch.Tensor, x_out: torch.Tensor,
+                 w2f: torch.Tensor, csum: torch.Tensor, b2: torch.Tensor, out2: torch.Tensor, *, ln_eps: float,
+                 act=ACT_NONE, n_split: int = 1, store_x: bool = True, col_block=0, col_block_stride=0, a_kblock=0,
+                 a_kblock_stride=0, tag=None) -> torch.Tensor:
+    """x_out = resid + a1 @ w1.T + b1 ; out2 = act(LayerNorm(x_out) @ W2.T + b2) with the LayerNorm folded into
+    (w2f, csum, b2) by `fold_layernorm` — one link of the router's block chain as one kernel (include/bya.h).
+    a1 [M,512] (or K-blocked, see `gemm`), w1 [512,512], w2f [N2,512], out2 [M,N2] (or column-blocked)."""
+    global LAUNCHES
+    for t, n in ((a1, "a1"), (w1, "w1"), (w2f, "w2f"), (resid, "resid"), (x_out, "x_out"), (out2, "out2")):
+        _bf16_2d(t, n)
+    M = a1.shape[0]
+    N2 = w2f.shape[0]
+    if tuple(w1.shape) != (512, 512) or w2f.shape[1] != 512 or (a1.shape[1] != (a_kblock if a_kblock else 512)) or \
+            tuple(resid.shape) != (M, 512) or tuple(x_out.shape) != (M, 512) or out2.shape[0] != M or \
+            out2.shape[1] != (col_block if col_block else N2):
+        raise RuntimeError(f"bya_b200.gemm_ln_gemm: shape mismatch a1{tuple(a1.shape)} w2f{tuple(w2f.shape)} out2{tuple(out2.shape)}")
+    _f32(csum, "csum"), _f32(b2, "b2")
+    if csum.numel() != N2 or b2.numel() != N2:
+        raise RuntimeError("bya_b200.gemm_ln_gemm: csum / b2 must have N2 elements")
+    ev = _prof(tag)
+    _bya.gemm_ln_gemm_bf16(a1, w1, b1, resid, x_out, int(store_x), w2f, csum, b2, float(ln_eps), act, out2, n_split, col_block,
+                           col_block_stride, a_kblock, a_kblock_stride)
+    if ev is not None:
+        ev.record()
+    LAUNCHES += 1
+    return out2
+
+
 def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, batch: int, seq: int,
                   heads: int, scale: float = 0.125, tag=None, score_bound_log2: Optional[float] = None,
                   seq_stride: Optional[int] = None) -> torch.Tensor:

@@ -90,6 +90,41 @@ typedef struct ByaGemmArgs {
 
 int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W, int ldw, const ByaGemmArgs* args);
 
+/* ---------------------------------------------------------------- one link of the router's block chain, fused
+ *   X    = resid + A1[M,512] · W1[512,512]^T + b1                      -> x_out (bf16; the LayerNorm input)
+ *   out2 = act( LayerNorm_512(X; eps, gamma, beta) · W2[N2,512]^T + b2 )
+ * Replaces `x = x + attn.to_out(...)` / `x = x + mlp[2](...)` followed by the NEXT sub-block's `normN(x)` and its
+ * to_q|to_k|to_v (or mlp[0] + GELU) in SpatialTemporalAttentionBlock.forward (models/router.py:474-491): three launches
+ * and two round trips of the [C*Nv, 512] activations become one kernel that keeps its 128 rows of X in tensor memory.
+ * The LayerNorm is folded (exact in real arithmetic): the caller passes W2f = bf16(W2 · diag(gamma)),
+ * csum[n] = sum_k float(W2f[n,k]) and b2[n] = bias2[n] + sum_k W2[n,k] * beta[k]; the kernel computes mean / rstd of the
+ * bf16-rounded X rows and forms rstd * (X · W2f^T - mean * csum) + b2.
+ * n_split > 1: the N2 columns are cut into n_split slices handled by different CTAs (the first GEMM is recomputed per
+ * slice; for small M); resid must then not alias x_out.  a_kblock / col_block: as in ByaGemmArgs (sequence-parallel
+ * receive / send buffers) for A1 and out2.  N2 % 128 == 0, N2 <= 1536. */
+typedef struct ByaChainArgs {
+  int M, N2;
+  int act;                 /* GEMM_ACT_* on out2 */
+  int n_split;             /* 0 / 1 -> off; (N2 / 128) % n_split == 0 */
+  const bya_bf16* b1;      /* [512] or NULL */
+  const bya_bf16* resid;   /* [M, ldr] */
+  int ldr;
+  bya_bf16* x_out;         /* [M, ldx]; may alias resid when n_split <= 1 */
+  int ldx;
+  int store_x;             /* 0: X is not written back (the caller only needs out2) */
+  float ln_eps;
+  const float* csum;       /* [N2] */
+  const float* b2;         /* [N2] folded bias */
+  bya_bf16* out2;          /* [M, ldc] (or the first column block, see col_block) */
+  int ldc;
+  int col_block;
+  long long col_block_stride;
+  int a_kblock;
+  long long a_kblock_stride;
+} ByaChainArgs;
+int bya_gemm_ln_gemm_bf16(void* stream, const void* A1, int lda, const void* W1, int ldw1, const void* W2f, int ldw2,
+                          const ByaChainArgs* args);
+
 /* ---------------------------------------------------------------- multi-head attention, head_dim 64, no mask
  * out[b*seq+n, h*64..] = softmax(Q_h K_h^T * scale) V_h ; q/k/v/out are row-major [batch*seq, ld] views whose head h
  * lives at columns [h*64, h*64+64) (i.e. column slices of the fused projection output).

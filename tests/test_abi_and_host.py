@@ -274,11 +274,11 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
     import subprocess
 
     import bya_b200  # noqa: F401
-    from bya_b200.lib import ByaDpmStepArgs, ByaGemmArgs
+    from bya_b200.lib import ByaChainArgs, ByaDpmStepArgs, ByaGemmArgs
 
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "bya.h")}"',
              'int main(void) {']
-    for name, st in (("ByaGemmArgs", ByaGemmArgs), ("ByaDpmStepArgs", ByaDpmStepArgs)):
+    for name, st in (("ByaGemmArgs", ByaGemmArgs), ("ByaChainArgs", ByaChainArgs), ("ByaDpmStepArgs", ByaDpmStepArgs)):
         lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
         for field, _ in st._fields_:
             lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
@@ -288,7 +288,7 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
     exe = tmp_path / "probe"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)
     got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
-    for name, st in (("ByaGemmArgs", ByaGemmArgs), ("ByaDpmStepArgs", ByaDpmStepArgs)):
+    for name, st in (("ByaGemmArgs", ByaGemmArgs), ("ByaChainArgs", ByaChainArgs), ("ByaDpmStepArgs", ByaDpmStepArgs)):
         assert int(got[name]) == ctypes.sizeof(st), name
         for field, _ in st._fields_:
             assert int(got[f"{name}.{field}"]) == getattr(st, field).offset, f"{name}.{field}"

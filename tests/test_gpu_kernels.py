@@ -50,6 +50,65 @@ def test_gemm_store(ops, M, N, K, act):
     assert rel(out, ref) < TOL
 
 
+def _chain_ref(a1, w1, b1, resid, w2, bias2, gamma, beta, eps, act):
+    """fp32 torch reference of one router link: X rounded to bf16 (it is stored / LayerNorm-ed as bf16 in the reference
+    module too), LayerNorm and the second linear in fp32."""
+    x = (resid.float() + a1.float() @ w1.float().t() + b1.float()).bfloat16()
+    y = F.layer_norm(x.float(), (512,), gamma.float(), beta.float(), eps) @ w2.float().t() + bias2.float()
+    return x, (F.gelu(y) if act == 2 else y)
+
+
+@pytest.mark.parametrize("M,N2,act,n_split", [(256, 512, 0, 1), (1000, 1536, 0, 1), (35100, 1536, 0, 1), (35100, 512, 2, 1),
+                                              (4388, 1536, 0, 3), (4388, 512, 2, 2), (77, 1536, 0, 12), (300, 384, 0, 3)])
+def test_gemm_ln_gemm_link(ops, M, N2, act, n_split):
+    """bya_gemm_ln_gemm_bf16 (the router's out-projection + residual + next LayerNorm + next projection as one kernel,
+    LayerNorm folded into the weights) vs the unfused fp32 arithmetic; rows with a large common offset exercise the
+    folded mean subtraction.  Tolerance: bf16 outputs, 1e-2 of abs-max (as the plain GEMM); X itself must match the
+    bf16-rounded fp32 value to one bf16 ulp."""
+    torch.manual_seed(11)
+    a1, w1, b1 = rnd(M, 512, s=0.5), rnd(512, 512, s=0.05), rnd(512, s=0.1)
+    resid = (torch.randn(M, 512, device=dev) + torch.randn(M, 1, device=dev) * 3.0).bfloat16()   # per-row mean offsets
+    w2, bias2 = rnd(N2, 512, s=0.05), rnd(N2, s=0.1)
+    gamma, beta = (1.0 + 0.2 * torch.randn(512, device=dev)).bfloat16(), (0.1 * torch.randn(512, device=dev)).bfloat16()
+    eps = 1e-5
+    x_ref, y_ref = _chain_ref(a1, w1, b1, resid, w2, bias2, gamma, beta, eps, act)
+    wf, csum, b2 = ops.fold_layernorm(w2, bias2, gamma, beta)
+    x_out = torch.zeros(M, 512, device=dev, dtype=torch.bfloat16)
+    out2 = torch.zeros(M, N2, device=dev, dtype=torch.bfloat16)
+    ops.gemm_ln_gemm(a1, w1, b1, resid, x_out, wf, csum, b2, out2, ln_eps=eps, act=act, n_split=n_split)
+    torch.cuda.synchronize()
+    assert rel(x_out, x_ref) < 5e-3
+    assert rel(out2, y_ref) < TOL
+    if n_split == 1:   # in place (resid aliases x_out), as the single-GPU router runs it: same bits
+        x2 = resid.clone()
+        out3 = torch.zeros_like(out2)
+        ops.gemm_ln_gemm(a1, w1, b1, x2, x2, wf, csum, b2, out3, ln_eps=eps, act=act)
+        assert torch.equal(x2, x_out) and torch.equal(out3, out2)
+
+
+def test_gemm_ln_gemm_blocked_operands(ops):
+    """The sequence-parallel forms: A1 given as K-blocks (all-to-all receive buffer), out2 scattered into column blocks
+    (send buffer) — same bits as the plain layout."""
+    torch.manual_seed(12)
+    M, N2, P = 900, 1536, 4
+    a1, w1, b1 = rnd(M, 512, s=0.5), rnd(512, 512, s=0.05), rnd(512, s=0.1)
+    resid, w2, bias2 = rnd(M, 512), rnd(N2, 512, s=0.05), rnd(N2, s=0.1)
+    gamma, beta = (1.0 + 0.2 * torch.randn(512, device=dev)).bfloat16(), (0.1 * torch.randn(512, device=dev)).bfloat16()
+    wf, csum, b2 = ops.fold_layernorm(w2, bias2, gamma, beta)
+    x0, y0 = torch.zeros(M, 512, device=dev, dtype=torch.bfloat16), torch.zeros(M, N2, device=dev, dtype=torch.bfloat16)
+    ops.gemm_ln_gemm(a1, w1, b1, resid, x0, wf, csum, b2, y0, ln_eps=1e-5)
+    kb = 512 // P
+    a_blk = a1.view(M, P, kb).permute(1, 0, 2).contiguous()          # [P][M][kb]
+    cb = N2 // P
+    y_blk = torch.zeros(P, M, cb, device=dev, dtype=torch.bfloat16)  # [dest][M][cb]
+    x1 = torch.zeros_like(x0)
+    ops.gemm_ln_gemm(a_blk[0], w1, b1, resid, x1, wf, csum, b2, y_blk[0], ln_eps=1e-5, n_split=3, a_kblock=kb,
+                     a_kblock_stride=M * kb, col_block=cb, col_block_stride=M * cb)
+    torch.cuda.synchronize()
+    assert torch.equal(x1, x0)
+    assert torch.equal(y_blk.permute(1, 0, 2).reshape(M, N2), y0)
+
+
 def test_gemm_strided_views(ops):
     """A, out given as column-slice views (row stride > width), as the engine uses them."""
     torch.manual_seed(2)
