@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(fa_threads(QT, NT), QT == 1 ? 2 : 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ FaArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   constexpr int FA_STAGES = fa_stages(QT);
   constexpr int FA_VSTAGES = fa_vstages(QT);
   uint8_t* sQ = smem;                                   // [QT][16 KB]

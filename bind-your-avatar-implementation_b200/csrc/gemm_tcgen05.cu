@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const GemmArgs p, const __grid_constant__ PeerMaps pmaps) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   using L = GemmSmem<BN, CTAS>;
   constexpr int kStages = L::kStages;
   constexpr int TM = BM * CTAS;                         // output rows per tile (per CTA pair when CTAS = 2)
@@ -101,7 +101,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiThreads * CTAS);   // the leader's copy also collects the peer's epilogue
+      mbar_init(&tempty_bar[s], 8 * CTAS);   // one arrive per epilogue warp; the leader's copy also collects the peer's
     }
     fence_barrier_init();
   }
@@ -285,6 +285,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       };
 
+      // The accumulator stage goes back to the MMA warp as soon as this warp's LAST chunk of it sits in registers —
+      // before that chunk's math and stores.  One arrive per warp, without a memory fence: only tensor memory changes
+      // hands (tcgen05.fence), the output stores are tracked by their bulk groups.
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CTAS == 2) mbar_arrive_remote_nofence(tempty_leader + uint32_t(as) * 8u);
+          else mbar_arrive(&tempty_bar[as]);
+        }
+      };
       if (p.mode == GEMM_EPI_SPLITK_F32) {
         // partial product of one k-range -> its own fp32 slice [ks][M][ldc] of the workspace (plain stores: the
         // reduction over the slices, bias and activation happen in bya_splitk_finalize in a FIXED order, so the
@@ -299,6 +310,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (CH == 32) tmem_ld_x32(taddr + c, r);
           else tmem_ld_x16(taddr + c, r);
           tmem_ld_wait();
+          if (ci == NCH - 1) release_acc();
           if (row_ok) {
 #pragma unroll
             for (int i = 0; i < CH; i += 4)
@@ -319,6 +331,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld_x32(taddr + c, r);
           tmem_ld_x32(taddr + c + 32, r + 32);
           tmem_ld_wait();
+          if (!(c + 64 < (half + 1) * HC && c + 64 < BN)) release_acc();   // last head of this warp
           const int col = col0 + c;
           float v[64];
 #pragma unroll
@@ -363,6 +376,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           store32(v, col);
           store32(v + 32, col + 32);
         }
+        if (half * HC >= BN) release_acc();   // BN = 64: the second warp of a lane quarter has no head to drain
       } else {
         const float* gate = nullptr;
         float rscale = p.alpha;
@@ -397,6 +411,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           tmem_ld_wait();
+          if (ci == NCH - 1) release_acc();
           const int col = col0 + c;
           float v[CH];
 #pragma unroll
@@ -426,9 +441,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           store32(v, col);
         }
       }
-      tc_fence_before();
-      if constexpr (CTAS == 2) mbar_arrive_remote(tempty_leader + uint32_t(as) * 8u);
-      else mbar_arrive(&tempty_bar[as]);
       if (warp == 4) GEMM_TRACE(7, ti);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
