@@ -23,13 +23,18 @@ BYA_DEVICE void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+BYA_DEVICE void ldmatrix_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
 constexpr int XA_WARPS = 8;
 constexpr int XA_TOK = XA_WARPS * 16;  // tokens per block
 
 // K  : [G][H][32][D]   (keys x head-dim, head-dim contiguous)
 // Vt : [G][H][D][32]   (V transposed: head-dim x keys, keys contiguous)  — both prepared once per generation
 template <int D, int C>
-__global__ void __launch_bounds__(XA_WARPS * 32)
+__global__ void __launch_bounds__(XA_WARPS * 32, D == 64 ? 3 : 2)
 xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ K,
                   const __nv_bfloat16* __restrict__ Vt, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                   int ldo, int heads, int tokens_per_frame, int kv_frames, float scale_log2, long long tok_begin,
@@ -118,18 +123,26 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
 
+    // B fragments come from shared memory with ldmatrix.x4: four 8x8 blocks per instruction, i.e. both halves of TWO
+    // k-steps — a quarter of the shared-memory instructions of per-fragment 32-bit loads (ncu, round 1: this kernel sat
+    // on the shared-memory pipe: mio / short-scoreboard stalls)
+    const int lrow = lane & 7, lcol = (lane >> 3) * 8;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
+      // characters none of this warp's 16 tokens is routed to contribute exactly zero: skip them (stage-2 hard masks:
+      // every token has one character, transformer.py:821-822 / :925-926 multiply the others by 0)
+      if (w != nullptr && __all_sync(0xffffffffu, wt0[c] == 0.f && wt1[c] == 0.f)) continue;
       // S = Q K_c^T : 16 x 32
       float s[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[c][nt * 8 + g][kk * 16 + 2 * t]);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[c][nt * 8 + g][kk * 16 + 8 + 2 * t]);
-          mma_bf16_16816(s[nt], qa[kk], b0, b1);
+        for (int k2 = 0; k2 < D / 32; ++k2) {
+          uint32_t bk[4];
+          ldmatrix_x4(bk, smem_u32(&sK[c][nt * 8 + lrow][k2 * 32 + lcol]));
+          mma_bf16_16816(s[nt], qa[2 * k2], bk[0], bk[1]);
+          mma_bf16_16816(s[nt], qa[2 * k2 + 1], bk[2], bk[3]);
         }
       }
       // softmax over the 32 keys of character c (rows g and g+8), fp32
@@ -159,19 +172,20 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
       l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
       const float f0 = wt0[c] / l0, f1 = wt1[c] / l1;
       // O += (w_c * P_c) V_c
+      uint32_t pa[2][4];
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
-        uint32_t pa[4];
-        pa[0] = pack_bf16x2(s[2 * kk][0] * f0, s[2 * kk][1] * f0);
-        pa[1] = pack_bf16x2(s[2 * kk][2] * f1, s[2 * kk][3] * f1);
-        pa[2] = pack_bf16x2(s[2 * kk + 1][0] * f0, s[2 * kk + 1][1] * f0);
-        pa[3] = pack_bf16x2(s[2 * kk + 1][2] * f1, s[2 * kk + 1][3] * f1);
+        pa[kk][0] = pack_bf16x2(s[2 * kk][0] * f0, s[2 * kk][1] * f0);
+        pa[kk][1] = pack_bf16x2(s[2 * kk][2] * f1, s[2 * kk][3] * f1);
+        pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0] * f0, s[2 * kk + 1][1] * f0);
+        pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2] * f1, s[2 * kk + 1][3] * f1);
+      }
 #pragma unroll
-        for (int nt = 0; nt < D / 8; ++nt) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sV[c][nt * 8 + g][kk * 16 + 2 * t]);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sV[c][nt * 8 + g][kk * 16 + 8 + 2 * t]);
-          mma_bf16_16816(o[nt], pa, b0, b1);
-        }
+      for (int nt = 0; nt < D / 8; ++nt) {
+        uint32_t bv[4];   // V^T rows nt*8.. (head-dims), keys 0-7 | 8-15 | 16-23 | 24-31
+        ldmatrix_x4(bv, smem_u32(&sV[c][nt * 8 + lrow][lcol]));
+        mma_bf16_16816(o[nt], pa[0], bv[0], bv[1]);
+        mma_bf16_16816(o[nt], pa[1], bv[2], bv[3]);
       }
     }
     // ---- store
@@ -199,10 +213,6 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
 constexpr int SA_WARPS = 4;
 constexpr int SA_PITCH = 72;   // bf16 elements per shared row: 144 B keeps ldmatrix and 16 B accesses conflict-free
 
-BYA_DEVICE void ldmatrix_x4(uint32_t* r, uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
 BYA_DEVICE void ldmatrix_x4_trans(uint32_t* r, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
