@@ -33,6 +33,7 @@ def test_sass_uses_blackwell_tensor_and_tma_paths(built):
 
     sass = subprocess.run(["cuobjdump", "-sass", LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass and "STTM" in sass
+    assert "UTCHMMA.2CTA" in sass      # CTA-pair GEMMs and the fused router link (tcgen05.mma.cta_group::2)
 
 
 def test_state_dict_keys_match_reference_checkpoint_contract():
@@ -157,6 +158,37 @@ def test_router_permutation_fold_identity():
     nat = q_out[0].transpose(0, 1).reshape(Nv, 2048)
     mine = torch.nn.functional.layer_norm(nat, (2048,), gamma[perm], beta[perm]) @ W[:, perm].t()
     assert float((ref[0] - mine).abs().max()) < 1e-9
+
+
+def test_layernorm_fold_of_the_fused_router_link_is_exact():
+    """`ops.fold_layernorm` (host side of bya_gemm_ln_gemm_bf16): LN(x) W^T + b == rstd * (x W'^T - mean * csum) + b' with
+    W' = W diag(gamma), csum = rowsum(W'), b' = b + W beta — checked in fp64 with the folded weight left unrounded, and the
+    bf16 rounding of W' bounded separately.  Also the column-slice policy for small row counts."""
+    import bya_b200  # noqa: F401
+    from bya_b200 import ops
+
+    torch.manual_seed(0)
+    M, N2 = 37, 256
+    x = torch.randn(M, 512, dtype=torch.float64) * 2 + torch.randn(M, 1, dtype=torch.float64) * 5
+    W, b = torch.randn(N2, 512, dtype=torch.float64) * 0.05, torch.randn(N2, dtype=torch.float64)
+    gamma, beta = 1 + 0.2 * torch.randn(512, dtype=torch.float64), 0.1 * torch.randn(512, dtype=torch.float64)
+    eps = 1e-5
+    ref = torch.nn.functional.layer_norm(x, (512,), gamma, beta, eps) @ W.t() + b
+    wf = W * gamma[None]
+    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    mine = rstd * (x @ wf.t() - mean * wf.sum(1)[None]) + (b + W @ beta)[None]
+    assert float((ref - mine).abs().max()) < 1e-10
+    wf16, csum, b2 = ops.fold_layernorm(W.float(), b.float(), gamma.float(), beta.float())
+    assert wf16.dtype == torch.bfloat16 and csum.dtype == torch.float32 and b2.dtype == torch.float32
+    assert torch.equal(csum, wf16.float().sum(1))                       # csum belongs to the ROUNDED weight
+    assert float((wf16.double() - wf).abs().max() / wf.abs().max()) < 2 ** -8
+    assert float((b2.double() - (b + W @ beta)).abs().max()) < 1e-5
+    # one CTA pair per 256-row tile: slices only while tiles x slices fit the 74 pairs, and only divisors of N2 / 128
+    assert ops.chain_n_split(35100, 1536) == 1 and ops.chain_n_split(4388, 1536) in (3, 4) and ops.chain_n_split(4388, 512) in (2, 4)
+    for rows, n2 in ((77, 1536), (300, 384), (4388, 512), (8775, 1536)):
+        ns = ops.chain_n_split(rows, n2)
+        assert (n2 // 128) % ns == 0 and ((rows + 255) // 256) * ns <= 74
 
 
 def test_mask_directory_loader_matches_reference_file_discovery(tmp_path):
