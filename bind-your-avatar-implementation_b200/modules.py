@@ -243,6 +243,7 @@ class PerceiverCrossAttention(nn.Module):
         self.to_q = nn.Linear(dim, inner, bias=False)
         self.to_kv = nn.Linear(kv_dim, inner * 2, bias=False)
         self.to_out = nn.Linear(inner, dim, bias=False)
+        self.return_weight_out = False   # forward(): also return the pre-softmax logits (dead in the reference flow)
 
     @torch.no_grad()
     def face_kv(self, x):
@@ -253,8 +254,10 @@ class PerceiverCrossAttention(nn.Module):
     @torch.no_grad()
     def forward(self, x, latents):
         """Reference signature: (face tokens [C,32,kv_dim], latents [C,Nv,dim]) -> (out [C,Nv,dim], weight_out,
-        q_out [C,heads,Nv,dh], k_out [C,heads,32,dh]).  `weight_out` (pre-softmax logits) is dead in the reference
-        (MultiIPRouter.forward ignores it, router.py:364) and is returned as None."""
+        q_out [C,heads,Nv,dh], k_out [C,heads,32,dh]).  `weight_out` (the pre-softmax logits [C,heads,Nv,32],
+        router.py:262-263) is dead in the reference flow (MultiIPRouter.forward ignores it, router.py:364): it is None unless
+        `self.return_weight_out` is set, in which case it is computed the way the router's score GEMM is (one dense GEMM
+        against the block-structured keys)."""
         from . import ops
 
         C, Nv, _ = latents.shape
@@ -273,7 +276,19 @@ class PerceiverCrossAttention(nn.Module):
                            self.dim_head ** -0.5)
             ops.gemm(a, self.to_out.weight, out[c])
             q_all.append(q.view(Nv, self.heads, self.dim_head).transpose(0, 1))
-        return out, None, torch.stack(q_all), k
+        w_out = None
+        if self.return_weight_out:
+            H, dh = self.heads, self.dim_head
+            w_out = torch.empty(C, H, Nv, 32, device=latents.device, dtype=latents.dtype)
+            for c in range(C):
+                kf = k[c].transpose(0, 1).reshape(32, H * dh).contiguous()          # [token, head-major features]
+                mat = torch.empty(32 * H, H * dh, device=kf.device, dtype=kf.dtype)
+                ops.router_keys_scatter(kf, mat, 1, H, dh)                           # row (token * H + h): key of head h
+                q_nat = q_all[c].transpose(0, 1).reshape(Nv, H * dh).contiguous()
+                sc = torch.empty(Nv, 32 * H, device=kf.device, dtype=kf.dtype)
+                ops.gemm(q_nat, mat, sc)
+                w_out[c] = (sc.float() * (dh ** -0.5)).view(Nv, 32, H).permute(2, 0, 1).to(w_out.dtype)
+        return out, w_out, torch.stack(q_all), k
 
 
 # --------------------------------------------------------------------------------------- router

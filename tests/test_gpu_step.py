@@ -263,6 +263,12 @@ def test_module_level_interfaces(c1):
     feat, q_ref, k_ref = restated.face_cross_attention(sd, "perceiver_cross_attention.0", face.float(), lat[:1].float())
     assert w_out is None and q_out.shape == (C, 16, Nv, 128) and k_out.shape == (C, 16, 32, 128)
     assert cos(out, feat) >= 0.999 and cos(q_out[0], q_ref[0]) >= 0.9995 and cos(k_out, k_ref) >= 0.9995
+    # the pre-softmax logits (router.py:262-263), on request: (q s)(k s)^T with s = dh^-1/4, per character and head
+    m.perceiver_cross_attention[0].return_weight_out = True
+    w_out = m.perceiver_cross_attention[0](face, lat)[1]
+    m.perceiver_cross_attention[0].return_weight_out = False
+    w_ref = torch.einsum("chnd,chkd->chnk", q_out.float(), k_out.float()) * (128 ** -0.5)
+    assert w_out.shape == (C, 16, Nv, 32) and cos(w_out, w_ref) >= 0.9999
     r = m.router(None, q_out, k_out, 0, False)
     r_ref = restated.router(sd, q_ref, k_ref, 0, cfg.frames, cfg.grid_h, cfg.grid_w)
     assert r.shape == (1, Nv, C) and float((r.float() - r_ref).abs().max()) < 0.03
