@@ -325,8 +325,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const float* sn = p.rope_sin + size_t(max(row - p.split_row, 0) + p.rope_row0) * 64;
         const int blk = p.qkv_block ? p.qkv_block : p.N;
         constexpr int HC = (BN / 2 >= 64) ? BN / 2 : 64;   // columns per warp (whole heads)
+        // Rotary values.  ncu (source page): with the full tables the rotation's first multiplies carried 23 % of all
+        // stall samples of the kernel — eight exposed L2 round trips per head, because the 32 scattered 16-byte loads per
+        // head and thread are issued in batches between the arithmetic (next to no L1 beside 220 KB of shared memory).
+        // With the packed table (each pair once) the 16 values of HALF a head are fetched before the accumulator is even
+        // loaded, and the other half while the first half is stored: their latency hides under the LayerNorm math.
+        // (Keeping the first half across the heads of a tile and fetching the second before the LayerNorm spilled: slower.)
+        // (use_pk is uniform over the CTA — store32 below synchronises the warp —; do_rot is per row)
+        const bool use_pk = p.rope_cs != nullptr && *p.rope_mismatch == 0;
+        const bool do_rot = is_video && row_ok;
+        const float4* rpk = reinterpret_cast<const float4*>(
+            p.rope_cs + ((use_pk && do_rot) ? size_t(max(row - p.split_row, 0) + p.rope_row0) * 64 : 0));
 #pragma unroll 1
         for (int c = half * HC; c < (half + 1) * HC && c < BN; c += 64) {
+          float4 rc[4], rs[4];   // cos / sin of the pairs of columns [0, 32) of the head
+          if (use_pk && do_rot) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { rc[i] = rpk[i]; rs[i] = rpk[8 + i]; }
+          }
           uint32_t r[64];
           tmem_ld_x32(taddr + c, r);
           tmem_ld_x32(taddr + c + 32, r + 32);
@@ -356,6 +372,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               v[i] = (v[i] - mean) * rstd * bf16_lo(ww) + bf16_lo(bb);
               v[i + 1] = (v[i + 1] - mean) * rstd * bf16_hi(ww) + bf16_hi(bb);
             }
+            const float qs = (!is_k && p.q_premul != 0.f) ? p.q_premul : 1.f;   // softmax scale * log2(e) folded into q
+            if (use_pk) {
+              auto rot16 = [&](float* x, const float4* cc, const float4* ss) {   // 32 columns = 16 pairs
+                if (!do_rot) return;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float cv[4] = {cc[i].x, cc[i].y, cc[i].z, cc[i].w};
+                  const float sv[4] = {ss[i].x, ss[i].y, ss[i].z, ss[i].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float x0 = x[8 * i + 2 * j], x1 = x[8 * i + 2 * j + 1];
+                    x[8 * i + 2 * j] = x0 * cv[j] - x1 * sv[j];
+                    x[8 * i + 2 * j + 1] = x1 * cv[j] + x0 * sv[j];
+                  }
+                }
+              };
+              rot16(v, rc, rs);
+              if (do_rot) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { rc[i] = rpk[4 + i]; rs[i] = rpk[12 + i]; }   // second half: in flight during the store
+              }
+              if (qs != 1.f) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= qs;
+              }
+              store32(v, col);
+              rot16(v + 32, rc, rs);
+              if (qs != 1.f) {
+#pragma unroll
+                for (int i = 32; i < 64; ++i) v[i] *= qs;
+              }
+              store32(v + 32, col + 32);
+              continue;
+            }
             if (is_video && row_ok) {
 #pragma unroll
               for (int i = 0; i < 64; i += 4) {
@@ -368,9 +418,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 v[i + 3] = x3 * c4.w + x2 * s4.w;
               }
             }
-            if (!is_k && p.q_premul != 0.f) {   // softmax scale * log2(e) folded into q (bya_attention_d64_bounded)
+            if (qs != 1.f) {
 #pragma unroll
-              for (int i = 0; i < 64; ++i) v[i] *= p.q_premul;
+              for (int i = 0; i < 64; ++i) v[i] *= qs;
             }
           }
           store32(v, col);

@@ -298,6 +298,29 @@ extern "C" int bya_gemv(void* stream, const void* W, const void* bias, const flo
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }
 
+namespace bya {
+__global__ void rope_pack_kernel(const float* __restrict__ cos, const float* __restrict__ sin, float* __restrict__ packed,
+                                 int* __restrict__ mismatch, int rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, pair)
+  if (idx >= (long long)rows * 32) return;
+  const long long r = idx >> 5;
+  const int i = int(idx & 31);
+  const float2 c = *reinterpret_cast<const float2*>(cos + r * 64 + 2 * i);
+  const float2 s = *reinterpret_cast<const float2*>(sin + r * 64 + 2 * i);
+  packed[r * 64 + i] = c.x;
+  packed[r * 64 + 32 + i] = s.x;
+  if (__float_as_uint(c.x) != __float_as_uint(c.y) || __float_as_uint(s.x) != __float_as_uint(s.y)) *mismatch = 1;
+}
+}  // namespace bya
+
+extern "C" int bya_rope_pack(void* stream, const float* cos, const float* sin, float* packed, int* mismatch, int rows) {
+  if (!cos || !sin || !packed || !mismatch || rows <= 0) return BYA_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(cos) | reinterpret_cast<uintptr_t>(sin) | reinterpret_cast<uintptr_t>(packed)) & 15) return BYA_ERR_ALIGN;
+  const long long n = (long long)rows * 32;
+  bya::rope_pack_kernel<<<unsigned((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cos, sin, packed, mismatch, rows);
+  return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
+}
+
 extern "C" int bya_timestep_features(void* stream, const int64_t* t, float* out, int batch, int dim) {
   if (!t || !out || batch <= 0 || dim <= 0 || dim % 2) return BYA_ERR_SHAPE;
   const int n = batch * dim / 2;

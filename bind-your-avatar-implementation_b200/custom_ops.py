@@ -45,10 +45,11 @@ def _op(schema: str):
 @_op("gemm_bf16(Tensor a, Tensor w, Tensor(a!) out, Tensor? bias, int act, int mode, Tensor? resid, Tensor? gate_a, "
      "Tensor? gate_b, int split_row, float alpha, Tensor? row_bias_scale, int qkv_block, float ln_eps, Tensor? rope_cos, "
      "Tensor? rope_sin, int rope_row0, Tensor? nq_w, Tensor? nq_b, Tensor? nk_w, Tensor? nk_b, int group_m, int col_block, "
-     "int col_block_stride, int a_kblock, int a_kblock_stride, float q_premul, int split_k, Tensor[]? peer_out) -> ()")
+     "int col_block_stride, int a_kblock, int a_kblock_stride, float q_premul, int split_k, Tensor[]? peer_out, "
+     "Tensor? rope_cs, Tensor? rope_mismatch) -> ()")
 def _gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, alpha, row_bias_scale, qkv_block, ln_eps,
                rope_cos, rope_sin, rope_row0, nq_w, nq_b, nk_w, nk_b, group_m, col_block, col_block_stride, a_kblock,
-               a_kblock_stride, q_premul, split_k, peer_out):
+               a_kblock_stride, q_premul, split_k, peer_out, rope_cs, rope_mismatch):
     g = ByaGemmArgs()
     g.M, g.N, g.K = a.shape[0], w.shape[0], w.shape[1]
     g.mode, g.act, g.group_m = mode, act, group_m
@@ -64,6 +65,7 @@ def _gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, alp
     g.a_kblock, g.a_kblock_stride = a_kblock, a_kblock_stride
     g.q_premul = q_premul
     g.split_k = split_k
+    g.rope_cs, g.rope_mismatch = _ptr(rope_cs), _ptr(rope_mismatch)
     if peer_out:   # push exchange: column block d goes to peer_out[d] (another GPU's memory), see include/bya.h
         for d, t in enumerate(peer_out):
             g.peer_out[d] = t.data_ptr()
@@ -127,6 +129,11 @@ def _layernorm_modulate(x, out, eps, gamma, beta, scale_a, shift_a, scale_b, shi
 def _gemv(w, bias, x, y, in_act, out_act):
     B, K = x.shape
     check(lib().bya_gemv(_stream(), _ptr(w), _ptr(bias), _ptr(x), _ptr(y), B, w.shape[0], K, in_act, out_act), "gemv")
+
+
+@_op("rope_pack(Tensor cos, Tensor sin, Tensor(a!) packed, Tensor(b!) mismatch) -> ()")
+def _rope_pack(cos, sin, packed, mismatch):
+    check(lib().bya_rope_pack(_stream(), _ptr(cos), _ptr(sin), _ptr(packed), _ptr(mismatch), cos.shape[0]), "rope_pack")
 
 
 @_op("timestep_features(Tensor t, Tensor(a!) out) -> ()")

@@ -646,6 +646,12 @@ class StepEngine:
                 idt = self._rope_identity = (torch.ones(Nv, 64, device=dev), torch.zeros(Nv, 64, device=dev))
             image_rotary_emb = idt
         cos, sin = (t.to(dev, torch.float32).contiguous() for t in image_rotary_emb)
+        # every (cos, sin) pair once per row for the QKV epilogue (diffusers' tables repeat each value twice; a table that
+        # does not is detected on the device and the epilogue then reads the full tables)
+        rope_packed = None
+        if cos.shape[1] == 64 and tuple(cos.shape) == tuple(sin.shape) and getattr(m, "packed_rope", True):
+            rope_packed = ops.rope_pack(cos, sin, ws.get("rope_cs", tuple(cos.shape), torch.float32),
+                                        ws.get("rope_mismatch", (1,), torch.int32))
         # joint positional table of the sincos / learned (CogVideoX-5B-I2V) configurations (transformer.py:370-392)
         pos_tab = m.patch_embed.table_for(Fr, Hl, Wl)
         if pos_tab is not None:
@@ -722,14 +728,14 @@ class StepEngine:
                 qpm = self.q_premul if sb is not None else 0.0
                 if P == 1:
                     ops.gemm(xn, L["w_qkv"], qkv, bias=L["b_qkv"], mode=ops.EPI_QKV, split_row=Tl, ln_eps=L["qk_eps"],
-                             rope=(cos, sin), nq=L["nq"], nk=L["nk"], q_premul=qpm)
+                             rope=(cos, sin), nq=L["nq"], nk=L["nk"], q_premul=qpm, rope_packed=rope_packed)
                     ops.attention_d64(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, 1, N, self.heads, tag="self_attention",
                                       score_bound_log2=sb)
                     ops.gemm(att, L["w_o"], x, bias=L["b_o"], mode=ops.EPI_RESIDUAL, resid=x, gate_a=eg, gate_b=g, split_row=Tl)
                 elif pg is None:
                     ops.gemm(xn, L["w_qkv_sp"], qkv_send[0], bias=L["b_qkv_sp"], mode=ops.EPI_QKV, split_row=Tl,
                              ln_eps=L["qk_eps"], rope=(cos, sin), rope_row0=v0, nq=L["nq"], nk=L["nk"], qkv_block=3 * Dl,
-                             col_block=3 * Dl, col_block_stride=R * 3 * Dl, q_premul=qpm, tag="qkv_gemm")
+                             col_block=3 * Dl, col_block_stride=R * 3 * Dl, q_premul=qpm, rope_packed=rope_packed, tag="qkv_gemm")
                     dist.all_to_all_single(qkv.view(P, R, 3 * Dl), qkv_send, group=self.sp_group)
                     ops.attention_d64(qkv[:, :Dl], qkv[:, Dl:2 * Dl], qkv[:, 2 * Dl:], o_send, 1, N, Hl_, tag="self_attention",
                                       score_bound_log2=sb)
@@ -739,7 +745,7 @@ class StepEngine:
                 else:
                     ops.gemm(xn, L["w_qkv_sp"], qkv_dst[0], bias=L["b_qkv_sp"], mode=ops.EPI_QKV, split_row=Tl,
                              ln_eps=L["qk_eps"], rope=(cos, sin), rope_row0=v0, nq=L["nq"], nk=L["nk"], qkv_block=3 * Dl,
-                             col_block=3 * Dl, q_premul=qpm, peer_out=qkv_dst, tag="qkv_gemm")
+                             col_block=3 * Dl, q_premul=qpm, peer_out=qkv_dst, rope_packed=rope_packed, tag="qkv_gemm")
                     pg.barrier()      # every rank's q|k|v block has landed in my `qkv`
                     ops.attention_d64_scatter(qkv[:, :Dl], qkv[:, Dl:2 * Dl], qkv[:, 2 * Dl:], o_dst, R, N, Hl_,
                                               tag="self_attention", score_bound_log2=sb)

@@ -25,6 +25,7 @@ class ByaGemmArgs(ctypes.Structure):
         ("a_kblock", ctypes.c_int), ("a_kblock_stride", ctypes.c_longlong),
         ("q_premul", ctypes.c_float), ("split_k", ctypes.c_int),
         ("peer_out", ctypes.c_void_p * 8),
+        ("rope_cs", ctypes.c_void_p), ("rope_mismatch", ctypes.c_void_p),
     ]
 
 

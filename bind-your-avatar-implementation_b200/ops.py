@@ -49,7 +49,8 @@ def _bf16_2d(t: torch.Tensor, name: str):
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=ACT_NONE, mode=EPI_STORE,
          resid=None, gate_a=None, gate_b=None, split_row=0, alpha=1.0, row_bias_scale=None,
          qkv_block=0, ln_eps=1e-6, rope=None, rope_row0=0, nq=None, nk=None, group_m=0, col_block=0,
-         col_block_stride=0, a_kblock=0, a_kblock_stride=0, q_premul=0.0, split_k=0, peer_out=None, tag=None) -> torch.Tensor:
+         col_block_stride=0, a_kblock=0, a_kblock_stride=0, q_premul=0.0, split_k=0, peer_out=None, rope_packed=None,
+         tag=None) -> torch.Tensor:
     """out = epilogue(a @ w.T); a [M,K], w [N,K], out [M,N] (row strides may exceed the width).
     With peer_out (a list of N/col_block [M, col_block] tensors, possibly views of OTHER ranks' memory): column block d is
     stored to peer_out[d]; pass out=peer_out[0].
@@ -78,10 +79,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, act=
     if mode == EPI_QKV:
         rope_cos, rope_sin = rope
         (nq_w, nq_b), (nk_w, nk_b) = nq, nk
+    rope_cs, rope_mis = rope_packed if (rope_packed is not None and mode == EPI_QKV) else (None, None)
     ev = _prof(tag)
     _bya.gemm_bf16(a, w, out, bias, act, mode, resid, gate_a, gate_b, split_row, float(alpha), row_bias_scale, qkv_block,
                    float(ln_eps), rope_cos, rope_sin, rope_row0, nq_w, nq_b, nk_w, nk_b, group_m, col_block, col_block_stride,
-                   a_kblock, a_kblock_stride, float(q_premul), split_k, peer_out)
+                   a_kblock, a_kblock_stride, float(q_premul), split_k, peer_out, rope_cs, rope_mis)
     if ev is not None:
         ev.record()
     LAUNCHES += 1
@@ -204,6 +206,20 @@ def gemv(w, bias, x, y, in_act=0, out_act=0):
     _bya.gemv(w, bias, x, y, in_act, out_act)
     _count()
     return y
+
+
+def rope_pack(cos: torch.Tensor, sin: torch.Tensor, packed: torch.Tensor, mismatch: torch.Tensor):
+    """cos / sin fp32 [rows, 64] -> packed fp32 [rows, 64] = [cos of the 32 pairs | sin of the 32 pairs]; `mismatch` (int32
+    [1], zeroed here) becomes 1 if the two values of some pair differ, in which case `gemm(..., rope_packed=...)` falls back
+    to the full tables on its own (device-side flag: no host synchronisation, safe inside a CUDA graph)."""
+    _f32(cos, "cos"), _f32(sin, "sin"), _f32(packed, "packed")
+    if tuple(cos.shape) != tuple(sin.shape) or cos.shape[1] != 64 or tuple(packed.shape) != tuple(cos.shape) or \
+            mismatch.dtype != torch.int32 or not mismatch.is_cuda:
+        raise RuntimeError("bya_b200.rope_pack: cos / sin / packed must be fp32 [rows, 64], mismatch CUDA int32")
+    memset_zero(mismatch)
+    _bya.rope_pack(cos, sin, packed, mismatch)
+    _count()
+    return packed, mismatch
 
 
 def timestep_features(t, out):

@@ -143,6 +143,7 @@ class BindyouravatarTransformer3DModel(nn.Module):
         self.bounded_attention = True  # joint self-attention without a running max when the qk-LayerNorm bounds |q.k|
         self.sp_cuda_graph = False   # also capture sequence-parallel steps (NCCL exchanges inside the graph)
         self.fused_router_links = os.environ.get("BYA_ROUTER_FUSED", "1") != "0"  # router chain: GEMM + LayerNorm + GEMM links as one kernel each
+        self.packed_rope = os.environ.get("BYA_ROPE_PACKED", "1") != "0"  # QKV epilogue reads the rotary table with every pair stored once
         self.use_cuda_graph = False  # replay the step as one CUDA graph per input geometry (engine.step_graphed)
         self._sp_group = None  # set by bya_b200.sp.enable(): Ulysses sequence parallelism over this process group
         self._cfg = None       # set by bya_b200.sp.enable(cfg_parallel=True): which CFG branch this rank computes

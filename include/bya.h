@@ -86,6 +86,13 @@ typedef struct ByaGemmArgs {
    * peer_out[d] — the base of a row-major [M, col_block] block with row stride ldc that may live in ANOTHER GPU's memory
    * (NVLink peer mapping) — instead of out + d * col_block_stride.  N / col_block <= BYA_MAX_PEERS. */
   void* peer_out[8];
+  /* GEMM_EPI_QKV, optional: the rotary table with every (cos, sin) pair stored ONCE per row — rope_cs [rows, 64] fp32 =
+   * [cos[0], cos[2], .., cos[62] | sin[0], sin[2], .., sin[62]] — built by bya_rope_pack, which also writes *rope_mismatch
+   * != 0 if some pair of the original tables differs (cos[2i] != cos[2i+1]; diffusers' tables repeat every value twice).
+   * When rope_cs != NULL and *rope_mismatch == 0 the epilogue reads 64 values per head and row instead of 128, early
+   * enough to hide their latency (same arithmetic, same bits); otherwise it reads rope_cos / rope_sin. */
+  const float* rope_cs;
+  const int* rope_mismatch;
 } ByaGemmArgs;
 
 int bya_gemm_bf16(void* stream, const void* A, int lda, const void* W, int ldw, const ByaGemmArgs* args);
@@ -184,6 +191,10 @@ int bya_layernorm_modulate(void* stream, const void* x, int ldx, void* out, int 
  * transformer.py:198,212,420) on the shared temb; also time_embedding.linear_1/2 (transformer.py:686). */
 int bya_gemv(void* stream, const void* W, const void* bias, const float* x, float* y, int batch, int N, int K,
              int in_act, int out_act);
+
+/* packed[r, i] = cos[r, 2i], packed[r, 32 + i] = sin[r, 2i] (i < 32); *mismatch (device int, zeroed by the caller) is set to 1
+ * if cos[r, 2i] != cos[r, 2i+1] or sin[r, 2i] != sin[r, 2i+1] anywhere.  See ByaGemmArgs.rope_cs. */
+int bya_rope_pack(void* stream, const float* cos, const float* sin, float* packed, int* mismatch, int rows);
 
 /* diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0) (transformer.py:680): out [batch, dim] fp32 */
 int bya_timestep_features(void* stream, const int64_t* t, float* out, int batch, int dim);

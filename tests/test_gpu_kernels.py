@@ -157,6 +157,28 @@ def test_gemm_qkv_layernorm_rope(ops):
 
     ref = torch.cat([ln_rope(y[:, :D], nq), ln_rope(y[:, D:2 * D], nk), y[:, 2 * D:]], 1)
     assert rel(out, ref) < 1.5e-2
+    # packed rotary table (bya_rope_pack: every pair once): same arithmetic, same bits — also with a row offset and the
+    # q pre-scale; a table whose pairs differ raises the device-side flag and the epilogue reads the full tables again
+    packed = ops.rope_pack(cos, sin, torch.empty_like(cos), torch.zeros(1, dtype=torch.int32, device=dev))
+    assert int(packed[1]) == 0 and torch.equal(packed[0][:, :32], cos[:, 0::2]) and torch.equal(packed[0][:, 32:], sin[:, 0::2])
+    out2 = torch.empty_like(out)
+    ops.gemm(a, w, out2, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos, sin), nq=nq, nk=nk, rope_packed=packed)
+    assert torch.equal(out2, out)
+    cos_o, sin_o = torch.cat([cos[:7] * 0 + 1, cos]), torch.cat([sin[:7] * 0, sin])     # 7 leading rows, skipped by rope_row0
+    pk_o = ops.rope_pack(cos_o, sin_o, torch.empty_like(cos_o), torch.zeros(1, dtype=torch.int32, device=dev))
+    o3, o4 = torch.empty_like(out), torch.empty_like(out)
+    ops.gemm(a, w, o3, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos_o, sin_o), rope_row0=7, nq=nq, nk=nk, q_premul=0.18)
+    ops.gemm(a, w, o4, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos_o, sin_o), rope_row0=7, nq=nq, nk=nk, q_premul=0.18,
+             rope_packed=pk_o)
+    assert torch.equal(o3, o4)
+    cos_bad = cos.clone()
+    cos_bad[5, 11] += 0.25                                                               # pair (10, 11) of row 5 now differs
+    pk_bad = ops.rope_pack(cos_bad, sin, torch.empty_like(cos), torch.zeros(1, dtype=torch.int32, device=dev))
+    assert int(pk_bad[1]) == 1
+    o5, o6 = torch.empty_like(out), torch.empty_like(out)
+    ops.gemm(a, w, o5, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos_bad, sin), nq=nq, nk=nk)
+    ops.gemm(a, w, o6, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos_bad, sin), nq=nq, nk=nk, rope_packed=pk_bad)
+    assert torch.equal(o5, o6) and not torch.equal(o5, out)
 
 
 def _gemm_ref_sampled(a, w, rows, cols):

@@ -25,9 +25,17 @@ def t(fn, n=20):
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / n
 
+packed = ops.rope_pack(cos, sin, torch.empty_like(cos), torch.zeros(1, dtype=torch.int32, device=dev))
+out2 = torch.empty_like(out)
+ops.gemm(a, w, out, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos, sin), nq=nq, nk=nk, q_premul=0.18)
+ops.gemm(a, w, out2, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos, sin), nq=nq, nk=nk, q_premul=0.18, rope_packed=packed)
+torch.cuda.synchronize()
+print("packed rotary table == full tables, bit for bit:", torch.equal(out, out2), "| mismatch flag", int(packed[1]))
 fl = 2.0 * M * 3 * D * K / 1e9
 t_qkv = t(lambda: ops.gemm(a, w, out, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos, sin), nq=nq, nk=nk, q_premul=0.18))
 t_st = t(lambda: ops.gemm(a, w, out, bias=b))
 t_norope = t(lambda: ops.gemm(a, w, out, bias=b, mode=ops.EPI_QKV, split_row=M, ln_eps=1e-6, rope=(cos, sin), nq=nq, nk=nk, q_premul=0.18))
 print(f"QKV epilogue with every row a text row (no RoPE loads): {t_norope:.3f} ms")
+t_pk = t(lambda: ops.gemm(a, w, out, bias=b, mode=ops.EPI_QKV, split_row=T, ln_eps=1e-6, rope=(cos, sin), nq=nq, nk=nk, q_premul=0.18, rope_packed=packed))
+print(f"QKV epilogue with the packed rotary table: {t_pk:.3f} ms = {fl / t_pk:.0f} TF/s")
 print(f"QKV epilogue {t_qkv:.3f} ms = {fl / t_qkv:.0f} TF/s | plain store {t_st:.3f} ms = {fl / t_st:.0f} TF/s | ratio {t_qkv / t_st:.3f}")
