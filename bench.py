@@ -299,17 +299,23 @@ def run_sp_check(args, cfg, dev, world):
     m = build_model(small, dev)
     inp = make_inputs(small, 4321, device=dev, dtype=torch.bfloat16)
     ref = m(**inp)[0].clone()
-    if args.cfg_parallel:
-        sp.enable(m, cfg_parallel=True)
-    else:
-        sp.enable(m, dist.group.WORLD)
-    out = m(**inp)[0]
-    torch.cuda.synchronize()
+    # the sharded step runs with NaN-filled scratch and exchange buffers: a row that is consumed without having been
+    # written (even with weight 0) turns the result into NaNs instead of hiding behind finite garbage
+    os.environ["BYA_POISON_SCRATCH"] = "1"
+    try:
+        if args.cfg_parallel:
+            sp.enable(m, cfg_parallel=True)
+        else:
+            sp.enable(m, dist.group.WORLD)
+        out = m(**inp)[0]
+        torch.cuda.synchronize()
+    finally:
+        os.environ["BYA_POISON_SCRATCH"] = "0"
     a, b = out.float().flatten().double(), ref.float().flatten().double()
     res = {"geometry": f"{small.frames}x{small.grid_h}x{small.grid_w} grid, {small.n_tokens} tokens, 2 layers, B={small.batch}, "
                        f"{'cfg2 x sp' + str(world // 2) if args.cfg_parallel else 'sp' + str(world)}",
            "max_abs": float((a - b).abs().max()), "cos": float((a @ b) / (a.norm() * b.norm() + 1e-30)),
-           "bit_identical": bool(torch.equal(out, ref)), "abs_max_ref": float(b.abs().max())}
+           "bit_identical": bool(torch.equal(out, ref)), "abs_max_ref": float(b.abs().max()), "scratch": "NaN-poisoned"}
     flag = torch.tensor([0 if res["cos"] >= 0.9999 else 1], device=dev)
     dist.all_reduce(flag)
     res["all_ranks_ok"] = int(flag.item()) == 0

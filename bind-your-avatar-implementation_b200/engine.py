@@ -21,6 +21,7 @@ There is no fallback path: every op above is a libbya.so kernel.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -70,6 +71,13 @@ class RouterPack:
         self.head_w, self.head_b = _bf(router.final_proj[0].weight.reshape(-1)), _bf(router.final_proj[0].bias)
 
 
+def poison_scratch() -> bool:
+    """BYA_POISON_SCRATCH=1: every scratch / exchange buffer is NaN-filled when it is allocated.  A kernel that consumes
+    rows nobody wrote (even with weight 0: 0 x NaN = NaN, while 0 x finite garbage is exactly 0 and goes unnoticed) then
+    shows up as NaNs in the result — the parity tests and bench.py's sp_check run with it."""
+    return os.environ.get("BYA_POISON_SCRATCH", "0") == "1"
+
+
 class _Workspace:
     """Named scratch buffers, allocated once per geometry (the C ABI never allocates)."""
 
@@ -81,6 +89,8 @@ class _Workspace:
         t = self.bufs.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(shape, device=self.device, dtype=dtype)
+            if poison_scratch() and t.dtype.is_floating_point:
+                t.fill_(float("nan"))
             self.bufs[name] = t
         return t
 
@@ -220,7 +230,10 @@ def run_router_sp(rp: RouterPack, rs: RouterShard, ws: _Workspace, q_all, kmat: 
             P, d, Fr, rs.hw, text_len, rows_per_rank, 2048), q_local, qf_ptrs)
         peer.barrier()           # the queries of my router positions have landed
     s_send = ws.get("rs_s_send", (P, M, Ws))              # [dest][local row][q|k|v heads of dest]
-    s_att = ws.get("rs_s_att", (CF * rs.hw_pad, Wo))
+    # zeroed once: the attention writes the hw real positions of every (c,f); the padding rows of the last shard are
+    # exchanged and projected like any row, and feed the NEXT block's K/V rows hw.., which the attention kernel loads
+    # with its last key tile (probability 0 — but 0 x NaN garbage is NaN)
+    s_att = ws.get_zeroed("rs_s_att", (CF * rs.hw_pad, Wo))
     rq = ws.get("rs_q", (R, 2048))
     ops.layernorm_modulate(qf, rq, eps=rp.eps, gamma=rp.nq_w, beta=rp.nq_b)
     rq2 = ws.get("rs_q2", (R, 2048))
@@ -592,8 +605,8 @@ class StepEngine:
 
             if N % P:
                 raise RuntimeError(f"bya_b200: {N} tokens are not divisible by the sequence-parallel size {P}")
-            if taps is not None:
-                raise RuntimeError("bya_b200: taps are a single-GPU debugging aid")
+            if taps is not None and not callable(taps):
+                raise RuntimeError("bya_b200: dict taps are a single-GPU debugging aid (a callable tap sees this rank's rows)")
         R = N // P                       # local rows
         n0 = rank * R                    # first local row (global index)
         Tl = min(max(T - n0, 0), R)      # local text rows

@@ -152,8 +152,16 @@ class PeerGroup:
         self.barriers = 0
 
     def _alloc(self, shape, dtype):
+        import torch.distributed as dist
+
+        from .engine import poison_scratch
+
         t = self.symm_mem.empty(*shape, dtype=dtype, device=self.device)
         hdl = self.symm_mem.rendezvous(t, self.group)
+        if poison_scratch() and dtype.is_floating_point:   # debugging aid (engine.poison_scratch): NaN until somebody writes
+            t.fill_(float("nan"))
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)                # nobody pushes into a buffer that is still being filled
         peers = [t if r == self.rank else hdl.get_buffer(r, tuple(shape), dtype) for r in range(self.P)]
         ptrs = torch.tensor([p.data_ptr() for p in peers], dtype=torch.int64, device=self.device)
         return t, peers, ptrs

@@ -305,6 +305,27 @@ def test_cuda_graph_replay_equals_eager(c1):
     assert torch.equal(g1, eager[1]) and torch.equal(g2, eager[1])
 
 
+@pytest.mark.parametrize("forced", [False, True])
+def test_no_kernel_consumes_unwritten_scratch(c1, monkeypatch, forced):
+    """BYA_POISON_SCRATCH=1 fills every scratch buffer with NaN when it is allocated: a kernel that reads a row nobody
+    wrote — even with weight 0 (masked key tiles, zero routing weights, padded rows) — would turn the prediction into
+    NaNs instead of hiding behind finite garbage.  The poisoned step must reproduce the normal step bit for bit."""
+    from bya_b200.synth import make_inputs
+
+    cfg, m, _ = c1
+    inp = make_inputs(cfg, 1234, device="cuda", dtype=torch.bfloat16, forced_masks=forced)
+    want = m(**inp)[0].clone()
+    monkeypatch.setenv("BYA_POISON_SCRATCH", "1")
+    m.invalidate()                       # new engine: every workspace is allocated (and poisoned) again
+    try:
+        got = m(**inp)[0].clone()
+    finally:
+        monkeypatch.setenv("BYA_POISON_SCRATCH", "0")
+        m.invalidate()
+    assert not got.float().isnan().any()
+    assert torch.equal(got, want)
+
+
 def test_weights_changed_in_place_are_repacked(c1):
     """`pipe.fuse_lora` (infer.py:279; util/utils.py:1038-1041 targets attn1.to_q / to_k) rewrites weights in place after
     the model was built: the packed copies (fused QKV, score bound, ...) must follow on the next forward, also in
