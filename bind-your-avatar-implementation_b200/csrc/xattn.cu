@@ -28,175 +28,275 @@ BYA_DEVICE void ldmatrix_x4(uint32_t* r, uint32_t addr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-constexpr int XA_WARPS = 8;
-constexpr int XA_TOK = XA_WARPS * 16;  // tokens per block
+constexpr int XA_WARPS = 4;
+#ifndef XA_BLOCKS
+#define XA_BLOCKS 3
+#endif
+
+BYA_DEVICE float xa_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+BYA_DEVICE float xa_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// packed fp32 pairs (one issue slot for two lanes of an accumulator register pair)
+BYA_DEVICE void xa_fma2(float& a0, float& a1, float b, float c) {   // a = a * b + c
+  asm("{\n\t.reg .b64 va, vb, vc;\n\tmov.b64 va, {%0, %1};\n\tmov.b64 vb, {%2, %2};\n\tmov.b64 vc, {%3, %3};\n\t"
+      "fma.rn.f32x2 va, va, vb, vc;\n\tmov.b64 {%0, %1}, va;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b), "f"(c));
+}
+BYA_DEVICE void xa_mul2(float& a0, float& a1, float b) {            // a = a * b
+  asm("{\n\t.reg .b64 va, vb;\n\tmov.b64 va, {%0, %1};\n\tmov.b64 vb, {%2, %2};\n\t"
+      "mul.rn.f32x2 va, va, vb;\n\tmov.b64 {%0, %1}, va;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b));
+}
+BYA_DEVICE void xa_add2(float& a0, float& a1, float b0, float b1) { // a = a + b
+  asm("{\n\t.reg .b64 va, vb;\n\tmov.b64 va, {%0, %1};\n\tmov.b64 vb, {%2, %3};\n\t"
+      "add.rn.f32x2 va, va, vb;\n\tmov.b64 {%0, %1}, va;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
 
 // K  : [G][H][32][D]   (keys x head-dim, head-dim contiguous)
 // Vt : [G][H][D][32]   (V transposed: head-dim x keys, keys contiguous)  — both prepared once per generation
-template <int D, int C>
-__global__ void __launch_bounds__(XA_WARPS * 32, D == 64 ? 3 : 2)
+//
+// Round-2 rewrite (the first version — K / V^T staged in shared memory per block, 4-byte q loads and 4-byte output
+// stores in the mma fragment layout — ran at 0.27 of the HBM roofline: mio / short-scoreboard / barrier stalls, and
+// every warp instruction touched 8 half-used sectors).  Now:
+//   * no block-level synchronisation at all: a WARP owns 16*MT tokens x the block's heads;
+//   * every operand moves in 16-byte pieces.  The contraction index of an MMA may be enumerated in any order as long as
+//     A and B agree, and so may the column index of B as long as the consumer of C knows it.  With
+//         k-slot (2t, 2t+1, 2t+8, 2t+9) of k-steps 2kk / 2kk+1   <->   elements 32kk + 8t + (0..3) / (4..7)
+//     thread (g, t) feeds both k-steps of Q K^T from ONE 16-byte piece of its q row and ONE of a K row; with
+//         column g of score tile nt   <->   key 8(g>>1) + 2nt + (g&1)
+//     the 8 scores a thread holds per row are the keys 8t..8t+7 — exactly one 16-byte piece of a V^T row for P V; with
+//         column g of output tile nt  <->   dim 32(nt>>2) + 8(g>>1) + 2(nt&3) + (g&1)
+//     a thread ends up with 8 CONSECUTIVE output dims per group of four tiles: one 16-byte store.
+//     K / V^T (10 MB in all) are read through L1 in their natural layouts — no staging, no ldmatrix — and the block
+//     prefetches the NEXT head's K / V^T lines into L1 (one line per thread) while it works on the current one: without
+//     it every first touch of a line is an exposed L2 round trip in front of an MMA (ncu: 23 % of the samples);
+//   * q rows stream in with cp.async (16 B, zero-fill for rows this rank does not own) one head ahead into a per-warp,
+//     XOR-swizzled landing buffer, after an L2 prefetch of the warp's whole q range (all heads of the block);
+//   * MT = 2 token tiles per warp at d = 64 share every K / V^T fragment (L1 wavefronts per token halved);
+//   * the softmax runs on ex2.approx / rcp.approx and packed f32x2 arithmetic (the kernel is issue-bound: ~1 600 warp
+//     instructions per 32 tokens x head before, the MMAs are 128 of them).
+// pf_mode: 0 no K / V^T prefetch, 1 prefetch.global.L1, 2 sector-touching loads.
+template <int D, int C, int MT>
+__global__ void __launch_bounds__(XA_WARPS * 32, XA_BLOCKS)
 xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ K,
                   const __nv_bfloat16* __restrict__ Vt, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                   int ldo, int heads, int tokens_per_frame, int kv_frames, float scale_log2, long long tok_begin,
-                  long long tok_count) {
-  constexpr int KP = D + 8;    // padded row of the K tile (bank-conflict-free fragment loads)
-  constexpr int VP = 32 + 8;   // padded row of the V^T tile
-  extern __shared__ __align__(16) uint8_t xa_smem[];
-  typedef __nv_bfloat16 (*KTile)[32][KP];
-  typedef __nv_bfloat16 (*VTile)[D][VP];
-  // two staging buffers: K / V^T of head h+1 stream in (cp.async) while head h is being computed
-  constexpr size_t kBufBytes = size_t(C) * 32 * KP * 2 + size_t(C) * D * VP * 2;
-  auto kbuf = [&](int i) { return reinterpret_cast<KTile>(xa_smem + i * kBufBytes); };
-  auto vbuf = [&](int i) { return reinterpret_cast<VTile>(xa_smem + i * kBufBytes + size_t(C) * 32 * KP * 2); };
+                  long long tok_count, int pf_mode) {
+  constexpr int ROWS = 16 * MT;   // tokens per warp
+  constexpr int CPR = D / 8;      // 16-byte chunks per q row of one head
+  constexpr int KK = D / 32;      // 16-byte pieces per thread and row (two k-steps each)
+  constexpr int NJ = ROWS * CPR / 32;   // cp.async pieces per lane and head
+  __shared__ __align__(128) uint4 qs[XA_WARPS][2][ROWS * CPR];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const uint32_t zr = uint32_t(pf_mode) >> 8;   // 0 (pf_mode is 0..2), opaque to the compiler
   const int frame = blockIdx.y;
-  const int tok0 = blockIdx.x * XA_TOK + warp * 16;               // within the frame
-  const int r0 = tok0 + g, r1 = tok0 + g + 8;                     // this thread's two rows (within the frame)
+  const int tokw = (blockIdx.x * XA_WARPS + warp) * ROWS;          // this warp's first token within the frame
   // global token index -> local row of q / w / out (this rank owns tokens [tok_begin, tok_begin + tok_count))
-  const long long blk_lo = (long long)frame * tokens_per_frame + blockIdx.x * XA_TOK;
-  if (blk_lo >= tok_begin + tok_count || blk_lo + XA_TOK <= tok_begin) return;  // no owned token in this block
-  const long long gl0 = (long long)frame * tokens_per_frame + r0 - tok_begin;
-  const long long gl1 = (long long)frame * tokens_per_frame + r1 - tok_begin;
-  const bool ok0 = r0 < tokens_per_frame && gl0 >= 0 && gl0 < tok_count;
-  const bool ok1 = r1 < tokens_per_frame && gl1 >= 0 && gl1 < tok_count;
-  const size_t n0 = size_t(ok0 ? gl0 : 0), n1 = size_t(ok1 ? gl1 : 0);
-
-  float wt0[C], wt1[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    wt0[c] = (w && ok0) ? w[n0 * C + c] : 1.f;
-    wt1[c] = (w && ok1) ? w[n1 * C + c] : 1.f;
-  }
-
-  // blockIdx.z = head group: one block per SM (143 blocks at the c2 size) left the kernel latency-bound (224 us
-  // against a 33 us HBM roofline); 4 head groups give every SM 3-4 resident blocks to overlap staging and math
+  const long long base = (long long)frame * tokens_per_frame + tokw - tok_begin;
+  auto row_ok = [&](int rr) { return tokw + rr < tokens_per_frame && base + rr >= 0 && base + rr < tok_count; };
   const int hpg = (heads + gridDim.z - 1) / gridDim.z;
   const int h_begin = blockIdx.z * hpg, h_end = min(heads, int(blockIdx.z + 1) * hpg);
-  // ---- stage K_h and V^T_h of every character (this block's frame) into buffer `b` with 16-byte cp.async
-  auto stage = [&](int h, int b) {
-    KTile dK = kbuf(b);
-    VTile dV = vbuf(b);
+  if (h_begin >= h_end) return;
+  // a warp without an owned token still helps with the block's K / V^T prefetches; it just has no rows
+  const bool warp_has_rows = tokw < tokens_per_frame && base + ROWS > 0 && base < tok_count;
+
+  // validity of the rows this thread computes (bit mt*2+j: row mt*16 + g + 8j) and copies (bit 8+j: row (lane + 32j) / CPR)
+  uint32_t vmask = 0;
+  float wt[MT][2][C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const size_t grp = (size_t(c) * kv_frames + frame) * heads + h;
-      const __nv_bfloat16* gk = K + grp * 32 * D;
-      for (int i = threadIdx.x; i < 32 * D / 8; i += blockDim.x) {
-        const int row = i / (D / 8), cc = i % (D / 8);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&dK[c][row][cc * 8])), "l"(gk + i * 8) : "memory");
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int rr = mt * 16 + g + 8 * j;
+      const bool okr = warp_has_rows && row_ok(rr);
+      vmask |= uint32_t(okr) << (mt * 2 + j);
+#pragma unroll
+      for (int c = 0; c < C; ++c) wt[mt][j][c] = okr ? (w ? w[size_t(base + rr) * C + c] : 1.f) : 0.f;
+    }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) vmask |= uint32_t(warp_has_rows && row_ok((lane + 32 * j) / CPR)) << (8 + j);
+
+  // ---- L2 prefetch of the warp's q rows for all heads of this block (contiguous per row)
+  if (warp_has_rows) {
+    const int lines = ((h_end - h_begin) * D * 2 + 127) / 128;
+    for (int rr = lane / 8; rr < ROWS; rr += 4) {
+      if (!row_ok(rr)) continue;
+      const char* p = reinterpret_cast<const char*>(q + size_t(base + rr) * ldq + h_begin * D);
+      for (int ln = lane & 7; ln < lines; ln += 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ln * 128));
+    }
+  }
+  // ---- K / V^T of head h (every character) -> L1, one 128-byte line per thread and round
+  auto prefetch_kv = [&](int h) {
+    if (pf_mode == 0) return;
+    constexpr int LPT = 32 * D * 2 / 128;          // lines per (character, K or V^T) tile
+    for (int i = threadIdx.x; i < C * 2 * LPT; i += XA_WARPS * 32) {
+      const int which = i / LPT, ln = i - which * LPT;
+      const size_t grp = (size_t(which >> 1) * kv_frames + frame) * heads + h;
+      const char* p = reinterpret_cast<const char*>(((which & 1) ? Vt : K) + grp * 32 * D) + ln * 128;
+      if (pf_mode == 1) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+      } else {
+        uint32_t d0, d1, d2, d3;   // one word per 32-byte sector
+        asm volatile("ld.global.nc.b32 %0, [%4];\n\tld.global.nc.b32 %1, [%4+32];\n\tld.global.nc.b32 %2, [%4+64];\n\t"
+                     "ld.global.nc.b32 %3, [%4+96];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "l"(p));
       }
-      const __nv_bfloat16* gv = Vt + grp * 32 * D;
-      for (int i = threadIdx.x; i < D * 32 / 8; i += blockDim.x) {
-        const int row = i / 4, cc = i % 4;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&dV[c][row][cc * 8])), "l"(gv + i * 8) : "memory");
-      }
+    }
+  };
+  // ---- q rows of head h -> landing buffer b (16-byte cp.async, chunk ^ 4 on odd rows keeps the fragment reads conflict-free)
+  const __nv_bfloat16* qlane = q + (lane % CPR) * 8;
+  auto issue = [&](int h, int b) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int rr = (lane + 32 * j) / CPR, ch = lane % CPR;
+      const bool v = (vmask >> (8 + j)) & 1u;
+      const __nv_bfloat16* src = v ? qlane + size_t(base + rr) * ldq + h * D : q;
+      const uint32_t dst = smem_u32(&qs[warp][b][rr * CPR + (ch ^ ((rr & 1) << 2))]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(v ? 16 : 0) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (h_begin < h_end) stage(h_begin, 0);
+  if (warp_has_rows) issue(h_begin, 0);
   for (int h = h_begin; h < h_end; ++h) {
     const int cur = (h - h_begin) & 1;
+    if (h + 1 < h_end) prefetch_kv(h + 1);
+    if (!warp_has_rows) continue;
+    __syncwarp();                 // every lane has taken its fragments of head h-1 out of buffer cur^1
     if (h + 1 < h_end) {
-      stage(h + 1, cur ^ 1);     // buffer cur^1 was last read in iteration h-1: every warp passed that iteration's trailing barrier
+      issue(h + 1, cur ^ 1);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();
-    KTile sK = kbuf(cur);
-    VTile sV = vbuf(cur);
+    __syncwarp();                 // ... and sees the pieces the other lanes fetched for head h
 
-    // ---- Q fragments of this warp's 16 tokens for head h (straight from global; zero for rows past the frame)
-    uint32_t qa[D / 16][4];
-    const __nv_bfloat16* q0 = q + n0 * ldq + h * D;
-    const __nv_bfloat16* q1 = q + n1 * ldq + h * D;
+    // A fragments of both k-steps of every 32-element slice: (row g | row g+8) x (elements 0-1 | 2-3) and (4-5 | 6-7)
+    uint32_t qa[MT][2 * KK][4];
 #pragma unroll
-    for (int kk = 0; kk < D / 16; ++kk) {
-      qa[kk][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 2 * t) : 0u;
-      qa[kk][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 2 * t) : 0u;
-      qa[kk][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 8 + 2 * t) : 0u;
-      qa[kk][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 8 + 2 * t) : 0u;
-    }
-
-    float o[D / 8][4];
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+      for (int kk = 0; kk < KK; ++kk) {
+        const uint4 r0 = qs[warp][cur][(mt * 16 + g) * CPR + ((kk * 4 + t) ^ ((g & 1) << 2))];
+        const uint4 r1 = qs[warp][cur][(mt * 16 + g + 8) * CPR + ((kk * 4 + t) ^ ((g & 1) << 2))];
+        // `^ zr` (a zero ptxas cannot see through): without it the fragment words keep living in the two 16-byte load
+        // results, whose register adjacency is not the MMA's, and every MMA gets its A quad copied together first
+        // (SASS: 4 moves in front of each of the 128 HMMAs)
+        qa[mt][2 * kk][0] = r0.x ^ zr, qa[mt][2 * kk][1] = r1.x ^ zr, qa[mt][2 * kk][2] = r0.y ^ zr, qa[mt][2 * kk][3] = r1.y ^ zr;
+        qa[mt][2 * kk + 1][0] = r0.z ^ zr, qa[mt][2 * kk + 1][1] = r1.z ^ zr, qa[mt][2 * kk + 1][2] = r0.w ^ zr,
+        qa[mt][2 * kk + 1][3] = r1.w ^ zr;
+      }
 
-    // B fragments come from shared memory with ldmatrix.x4: four 8x8 blocks per instruction, i.e. both halves of TWO
-    // k-steps — a quarter of the shared-memory instructions of per-fragment 32-bit loads (ncu, round 1: this kernel sat
-    // on the shared-memory pipe: mio / short-scoreboard stalls)
-    const int lrow = lane & 7, lcol = (lane >> 3) * 8;
+    float o[MT][D / 8][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) o[mt][i][0] = o[mt][i][1] = o[mt][i][2] = o[mt][i][3] = 0.f;
+
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      // characters none of this warp's 16 tokens is routed to contribute exactly zero: skip them (stage-2 hard masks:
+      // characters none of this warp's tokens is routed to contribute exactly zero: skip them (stage-2 hard masks:
       // every token has one character, transformer.py:821-822 / :925-926 multiply the others by 0)
-      if (w != nullptr && __all_sync(0xffffffffu, wt0[c] == 0.f && wt1[c] == 0.f)) continue;
-      // S = Q K_c^T : 16 x 32
-      float s[4][4];
+      bool none = true;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      for (int mt = 0; mt < MT; ++mt) none = none && wt[mt][0][c] == 0.f && wt[mt][1][c] == 0.f;
+      if (__all_sync(0xffffffffu, none)) continue;
+      const size_t grp = (size_t(c) * kv_frames + frame) * heads + h;
+      const __nv_bfloat16* Kc = K + grp * 32 * D + 8 * t + (8 * (g >> 1) + (g & 1)) * D;
+      const __nv_bfloat16* Vc = Vt + grp * 32 * D + 8 * t + (8 * (g >> 1) + (g & 1)) * 32;
+      // S = Q K_c^T : (16 MT) x 32; column g of tile nt is key 8(g>>1) + 2nt + (g&1)
+      float s[MT][4][4];
 #pragma unroll
-        for (int k2 = 0; k2 < D / 32; ++k2) {
-          uint32_t bk[4];
-          ldmatrix_x4(bk, smem_u32(&sK[c][nt * 8 + lrow][k2 * 32 + lcol]));
-          mma_bf16_16816(s[nt], qa[2 * k2], bk[0], bk[1]);
-          mma_bf16_16816(s[nt], qa[2 * k2 + 1], bk[2], bk[3]);
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+      // (k-slice outermost, score tile innermost: an A quad is put together once and feeds four MMAs)
+#pragma unroll
+      for (int kk = 0; kk < KK; ++kk) {
+        uint4 b[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) b[nt] = __ldg(reinterpret_cast<const uint4*>(Kc + 2 * nt * D + kk * 32));
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(s[mt][nt], qa[mt][2 * kk], b[nt].x, b[nt].y);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(s[mt][nt], qa[mt][2 * kk + 1], b[nt].z, b[nt].w);
         }
       }
-      // softmax over the 32 keys of character c (rows g and g+8), fp32
-      float m0 = -INFINITY, m1 = -INFINITY;
+      // softmax over the 32 keys of character c (rows g and g+8 of every token tile), fp32; w_c / sum folded into P
+      uint32_t pa[MT][2][4];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-      }
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      float l0 = 0.f, l1 = 0.f;
+      for (int mt = 0; mt < MT; ++mt) {
+        float f[2];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        s[nt][0] = exp2f((s[nt][0] - m0) * scale_log2);
-        s[nt][1] = exp2f((s[nt][1] - m0) * scale_log2);
-        s[nt][2] = exp2f((s[nt][2] - m1) * scale_log2);
-        s[nt][3] = exp2f((s[nt][3] - m1) * scale_log2);
-        l0 += s[nt][0] + s[nt][1];
-        l1 += s[nt][2] + s[nt][3];
-      }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      const float f0 = wt0[c] / l0, f1 = wt1[c] / l1;
-      // O += (w_c * P_c) V_c
-      uint32_t pa[2][4];
+        for (int j = 0; j < 2; ++j) {          // j = 0: row g (accumulator lanes 0, 1); j = 1: row g + 8 (lanes 2, 3)
+          float m = fmaxf(fmaxf(s[mt][0][2 * j], s[mt][0][2 * j + 1]), fmaxf(s[mt][1][2 * j], s[mt][1][2 * j + 1]));
+          m = fmaxf(m, fmaxf(fmaxf(s[mt][2][2 * j], s[mt][2][2 * j + 1]), fmaxf(s[mt][3][2 * j], s[mt][3][2 * j + 1])));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          const float nm = -m * scale_log2;
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        pa[kk][0] = pack_bf16x2(s[2 * kk][0] * f0, s[2 * kk][1] * f0);
-        pa[kk][1] = pack_bf16x2(s[2 * kk][2] * f1, s[2 * kk][3] * f1);
-        pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0] * f0, s[2 * kk + 1][1] * f0);
-        pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2] * f1, s[2 * kk + 1][3] * f1);
+          for (int nt = 0; nt < 4; ++nt) {
+            xa_fma2(s[mt][nt][2 * j], s[mt][nt][2 * j + 1], scale_log2, nm);
+            s[mt][nt][2 * j] = xa_ex2(s[mt][nt][2 * j]);
+            s[mt][nt][2 * j + 1] = xa_ex2(s[mt][nt][2 * j + 1]);
+          }
+          float l0 = s[mt][0][2 * j], l1 = s[mt][0][2 * j + 1];
+#pragma unroll
+          for (int nt = 1; nt < 4; ++nt) xa_add2(l0, l1, s[mt][nt][2 * j], s[mt][nt][2 * j + 1]);
+          float l = l0 + l1;
+          l += __shfl_xor_sync(0xffffffffu, l, 1);
+          l += __shfl_xor_sync(0xffffffffu, l, 2);
+          f[j] = wt[mt][j][c] * xa_rcp(l);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) xa_mul2(s[mt][nt][2 * j], s[mt][nt][2 * j + 1], f[j]);
+        }
+        // k-slots (2t, 2t+1 | 2t+8, 2t+9) of k-step kk hold the keys 8t + 4kk + (0, 1 | 2, 3): tiles 2kk and 2kk+1
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          pa[mt][kk][0] = pack_bf16x2(s[mt][2 * kk][0], s[mt][2 * kk][1]);
+          pa[mt][kk][1] = pack_bf16x2(s[mt][2 * kk][2], s[mt][2 * kk][3]);
+          pa[mt][kk][2] = pack_bf16x2(s[mt][2 * kk + 1][0], s[mt][2 * kk + 1][1]);
+          pa[mt][kk][3] = pack_bf16x2(s[mt][2 * kk + 1][2], s[mt][2 * kk + 1][3]);
+        }
       }
+      // O += (w_c * P_c) V_c; column g of tile nt is head-dim 32(nt>>2) + 8(g>>1) + 2(nt&3) + (g&1)
 #pragma unroll
       for (int nt = 0; nt < D / 8; ++nt) {
-        uint32_t bv[4];   // V^T rows nt*8.. (head-dims), keys 0-7 | 8-15 | 16-23 | 24-31
-        ldmatrix_x4(bv, smem_u32(&sV[c][nt * 8 + lrow][lcol]));
-        mma_bf16_16816(o[nt], pa[0], bv[0], bv[1]);
-        mma_bf16_16816(o[nt], pa[1], bv[2], bv[3]);
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(Vc + (32 * (nt >> 2) + 2 * (nt & 3)) * 32));   // keys 8t .. 8t+7
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(o[mt][nt], pa[mt][0], b.x, b.y);
+          mma_bf16_16816(o[mt][nt], pa[mt][1], b.z, b.w);
+        }
       }
     }
-    // ---- store
-    __nv_bfloat16* d0 = out + n0 * ldo + h * D;
-    __nv_bfloat16* d1 = out + n1 * ldo + h * D;
+    // ---- store: 8 consecutive dims per thread and group of four tiles
 #pragma unroll
-    for (int nt = 0; nt < D / 8; ++nt) {
-      if (ok0) *reinterpret_cast<uint32_t*>(d0 + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0], o[nt][1]);
-      if (ok1) *reinterpret_cast<uint32_t*>(d1 + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2], o[nt][3]);
-    }
-    __syncthreads();   // everyone is done with buffer `cur` before the next iteration refills it
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (!((vmask >> (mt * 2 + j)) & 1u)) continue;
+        __nv_bfloat16* d = out + size_t(base + mt * 16 + g + 8 * j) * ldo + h * D + 8 * t;
+#pragma unroll
+        for (int G = 0; G < D / 32; ++G) {
+          uint4 v;
+          v.x = pack_bf16x2(o[mt][4 * G][2 * j], o[mt][4 * G][2 * j + 1]);
+          v.y = pack_bf16x2(o[mt][4 * G + 1][2 * j], o[mt][4 * G + 1][2 * j + 1]);
+          v.z = pack_bf16x2(o[mt][4 * G + 2][2 * j], o[mt][4 * G + 2][2 * j + 1]);
+          v.w = pack_bf16x2(o[mt][4 * G + 3][2 * j], o[mt][4 * G + 3][2 * j + 1]);
+          __stcs(reinterpret_cast<uint4*>(d + 32 * G), v);
+        }
+      }
   }
 }
 
@@ -399,33 +499,32 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
   if (!q || !K || !Vt || !out || tokens <= 0 || heads <= 0 || kv_frames <= 0 || total_tokens % kv_frames ||
       tok_begin < 0 || tok_begin + tokens > total_tokens)
     return BYA_ERR_SHAPE;
-  if (ldq % 2 || ldo % 2) return BYA_ERR_ALIGN;
+  // every q / out / K / V^T access is a 16-byte piece
+  if (ldq % 8 || ldo % 8) return BYA_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(K) |
+       reinterpret_cast<uintptr_t>(Vt)) & 15)
+    return BYA_ERR_ALIGN;
   const int tpf = int(total_tokens / kv_frames);
-  static int xa_hpg = 0;   // heads per block (tuning knob BYA_XA_HPG)
-  if (!xa_hpg) { const char* e = std::getenv("BYA_XA_HPG"); xa_hpg = e ? std::atoi(e) : 4; if (xa_hpg < 1) xa_hpg = 4; }
-  dim3 grid((tpf + XA_TOK - 1) / XA_TOK, kv_frames, (heads + xa_hpg - 1) / xa_hpg);
+  static int xa_hpg = -1;   // heads per block (tuning knob BYA_XA_HPG; default 4 at d = 64, 2 at d = 128)
+  if (xa_hpg < 0) { const char* e = std::getenv("BYA_XA_HPG"); xa_hpg = e ? std::atoi(e) : 0; if (xa_hpg < 0) xa_hpg = 0; }
+  const int hpg = xa_hpg ? xa_hpg : (head_dim == 64 ? 4 : 2);
+  static int xa_pf = -1;    // K / V^T L1 prefetch of the next head (BYA_XA_PF: 0 off, 1 prefetch.global.L1, 2 sector-touching loads)
+  if (xa_pf < 0) { const char* e = std::getenv("BYA_XA_PF"); xa_pf = e ? std::atoi(e) : 1; if (xa_pf < 0 || xa_pf > 2) xa_pf = 1; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const float sl2 = scale * 1.4426950408889634f;
-#define BYA_XA(D_, C_)                                                                                            \
+#define BYA_XA(D_, C_, MT_)                                                                                       \
   do {                                                                                                            \
-    constexpr int smem = 2 * (C_ * 32 * (D_ + 8) * 2 + C_ * D_ * 40 * 2);   /* two staging buffers */             \
-    static bool attr = false;                                                                                     \
-    if (!attr) {                                                                                                  \
-      if (cudaFuncSetAttribute(xattn_kv32_kernel<D_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=   \
-          cudaSuccess)                                                                                            \
-        return BYA_ERR_CUDA;                                                                                      \
-      attr = true;                                                                                                \
-    }                                                                                                             \
-    xattn_kv32_kernel<D_, C_><<<grid, XA_WARPS * 32, smem, s>>>(                                                  \
+    dim3 grid((tpf + XA_WARPS * 16 * MT_ - 1) / (XA_WARPS * 16 * MT_), kv_frames, (heads + hpg - 1) / hpg);       \
+    xattn_kv32_kernel<D_, C_, MT_><<<grid, XA_WARPS * 32, 0, s>>>(                                                \
         (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)K, (const __nv_bfloat16*)Vt, w, (__nv_bfloat16*)out,  \
-        ldo, heads, tpf, kv_frames, sl2, tok_begin, tokens);                                                      \
+        ldo, heads, tpf, kv_frames, sl2, tok_begin, tokens, xa_pf);                                               \
   } while (0)
-  if (head_dim == 64 && chars == 1) BYA_XA(64, 1);
-  else if (head_dim == 64 && chars == 2) BYA_XA(64, 2);
-  else if (head_dim == 64 && chars == 3) BYA_XA(64, 3);
-  else if (head_dim == 128 && chars == 1) BYA_XA(128, 1);
-  else if (head_dim == 128 && chars == 2) BYA_XA(128, 2);
-  else if (head_dim == 128 && chars == 3) BYA_XA(128, 3);
+  if (head_dim == 64 && chars == 1) BYA_XA(64, 1, 2);
+  else if (head_dim == 64 && chars == 2) BYA_XA(64, 2, 2);
+  else if (head_dim == 64 && chars == 3) BYA_XA(64, 3, 2);
+  else if (head_dim == 128 && chars == 1) BYA_XA(128, 1, 1);
+  else if (head_dim == 128 && chars == 2) BYA_XA(128, 2, 1);
+  else if (head_dim == 128 && chars == 3) BYA_XA(128, 3, 1);
   else return BYA_ERR_SHAPE;
 #undef BYA_XA
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;

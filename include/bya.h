@@ -164,6 +164,7 @@ int bya_attention_d64_scatter(void* stream, const void* q, const void* k, const 
  * out[n, h*d..] = sum_c w[n,c] * softmax_k(scale * q[n,h,:].K[g][h][k][:]) @ V[g][h],  g = c*kv_frames + n/(tokens/kv_frames)
  * K  : [chars*kv_frames][heads][32][head_dim],  Vt : [chars*kv_frames][heads][head_dim][32]  (V transposed), bf16.
  * w  : [tokens, chars] fp32 routing / audio weights (NULL -> 1).  head_dim in {64,128}, chars in {1,2,3}.
+ * q, out, K, Vt 16-byte aligned, ldq / ldo multiples of 8 (every access is a 16-byte piece; BYA_ERR_ALIGN otherwise).
  * Replaces the attention core + routed blend of PerceiverCrossAttention (router.py:256-273 with transformer.py:821-822)
  * and of the audio cross-attention (audio_model.py:253-256 with transformer.py:925-926). */
 /* Sequence-parallel use: q/w/out hold only the `tokens` video tokens [tok_begin, tok_begin+tokens) of `total_tokens`
