@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbya.so")
-SOURCES = ["abi.cu", "gemm_tcgen05.cu", "chain_tcgen05.cu", "fa_tcgen05.cu", "rowops.cu", "xattn.cu", "mask3d.cu", "denoise_glue.cu", "prologue.cu", "peer.cu"]
+SOURCES = ["abi.cu", "gemm_tcgen05.cu", "chain_tcgen05.cu", "fa_tcgen05.cu", "rowops.cu", "xattn.cu", "xattn_tc.cu", "mask3d.cu", "denoise_glue.cu", "prologue.cu", "peer.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

@@ -29,9 +29,6 @@ BYA_DEVICE void ldmatrix_x4(uint32_t* r, uint32_t addr) {
 }
 
 constexpr int XA_WARPS = 4;
-#ifndef XA_BLOCKS
-#define XA_BLOCKS 3
-#endif
 
 BYA_DEVICE float xa_ex2(float x) {
   float y;
@@ -84,7 +81,7 @@ BYA_DEVICE void xa_add2(float& a0, float& a1, float b0, float b1) { // a = a + b
 //   * the softmax runs on ex2.approx / rcp.approx and packed f32x2 arithmetic (the kernel is issue-bound: ~1 600 warp
 //     instructions per 32 tokens x head before, the MMAs are 128 of them).
 // pf_mode: 0 no K / V^T prefetch, 1 prefetch.global.L1, 2 sector-touching loads.
-template <int D, int C, int MT>
+template <int D, int C, int MT, int XA_BLOCKS, bool STAGE>
 __global__ void __launch_bounds__(XA_WARPS * 32, XA_BLOCKS)
 xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ K,
                   const __nv_bfloat16* __restrict__ Vt, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
@@ -94,7 +91,12 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
   constexpr int CPR = D / 8;      // 16-byte chunks per q row of one head
   constexpr int KK = D / 32;      // 16-byte pieces per thread and row (two k-steps each)
   constexpr int NJ = ROWS * CPR / 32;   // cp.async pieces per lane and head
-  __shared__ __align__(128) uint4 qs[XA_WARPS][2][ROWS * CPR];
+  // dynamic shared memory: per-warp q landing buffers [XA_WARPS][2][ROWS * CPR], then (STAGE) the block's K / V^T
+  // buffers [2][C][K: 32 rows x CPR chunks, chunk ^ 4 on odd rows | V^T: D rows x 4 chunks, linear]
+  extern __shared__ __align__(128) uint4 xa_dyn[];
+  uint4 (*qs)[2][ROWS * CPR] = reinterpret_cast<uint4 (*)[2][ROWS * CPR]>(xa_dyn);
+  constexpr int KVC = 4 * D;                       // 16-byte chunks of one K (or V^T) tile of one character
+  uint4* kvs = xa_dyn + XA_WARPS * 2 * ROWS * CPR;   // [2][C][2][KVC]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -165,19 +167,49 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (warp_has_rows) issue(h_begin, 0);
+  // ---- (STAGE) K / V^T of head h, every character -> shared buffer b, by the whole block
+  auto stage_kv = [&](int h, int b) {
+    for (int i = threadIdx.x; i < C * 2 * KVC; i += XA_WARPS * 32) {
+      const int which = i / KVC, idx = i - which * KVC;   // which = 2 c + (0: K, 1: V^T)
+      const size_t grp = (size_t(which >> 1) * kv_frames + frame) * heads + h;
+      const __nv_bfloat16* src = ((which & 1) ? Vt : K) + grp * 32 * D + idx * 8;
+      int d = idx;
+      if (!(which & 1)) { const int row = idx / CPR, ch = idx % CPR; d = row * CPR + (ch ^ ((row & 1) << 2)); }
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&kvs[(b * C * 2 + which) * KVC + d])), "l"(src) : "memory");
+    }
+  };
+  if constexpr (STAGE) {
+    stage_kv(h_begin, 0);
+    if (warp_has_rows) issue(h_begin, 0);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+    if (warp_has_rows) issue(h_begin, 0);
+  }
   for (int h = h_begin; h < h_end; ++h) {
     const int cur = (h - h_begin) & 1;
-    if (h + 1 < h_end) prefetch_kv(h + 1);
-    if (!warp_has_rows) continue;
-    __syncwarp();                 // every lane has taken its fragments of head h-1 out of buffer cur^1
-    if (h + 1 < h_end) {
-      issue(h + 1, cur ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
+    if constexpr (STAGE) {
+      // one group per head holds this thread's q pieces AND its share of the block's K / V^T; one barrier per head:
+      // head h has landed for everyone, and everyone is done with head h-1 (whose buffers the next copies overwrite)
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (h + 1 < h_end) {
+        stage_kv(h + 1, cur ^ 1);
+        if (warp_has_rows) issue(h + 1, cur ^ 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      if (!warp_has_rows) continue;
+    } else {
+      if (h + 1 < h_end) prefetch_kv(h + 1);
+      if (!warp_has_rows) continue;
+      __syncwarp();                 // every lane has taken its fragments of head h-1 out of buffer cur^1
+      if (h + 1 < h_end) {
+        issue(h + 1, cur ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncwarp();                 // ... and sees the pieces the other lanes fetched for head h
     }
-    __syncwarp();                 // ... and sees the pieces the other lanes fetched for head h
 
     // A fragments of both k-steps of every 32-element slice: (row g | row g+8) x (elements 0-1 | 2-3) and (4-5 | 6-7)
     uint32_t qa[MT][2 * KK][4];
@@ -223,7 +255,12 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
       for (int kk = 0; kk < KK; ++kk) {
         uint4 b[4];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) b[nt] = __ldg(reinterpret_cast<const uint4*>(Kc + 2 * nt * D + kk * 32));
+        for (int nt = 0; nt < 4; ++nt) {
+          if constexpr (STAGE)
+            b[nt] = kvs[(cur * C * 2 + 2 * c) * KVC + (8 * (g >> 1) + 2 * nt + (g & 1)) * CPR + ((kk * 4 + t) ^ ((g & 1) << 2))];
+          else
+            b[nt] = __ldg(reinterpret_cast<const uint4*>(Kc + 2 * nt * D + kk * 32));
+        }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -272,7 +309,11 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
       // O += (w_c * P_c) V_c; column g of tile nt is head-dim 32(nt>>2) + 8(g>>1) + 2(nt&3) + (g&1)
 #pragma unroll
       for (int nt = 0; nt < D / 8; ++nt) {
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(Vc + (32 * (nt >> 2) + 2 * (nt & 3)) * 32));   // keys 8t .. 8t+7
+        uint4 b;   // keys 8t .. 8t+7 of that head-dim
+        if constexpr (STAGE)
+          b = kvs[(cur * C * 2 + 2 * c + 1) * KVC + (32 * (nt >> 2) + 8 * (g >> 1) + 2 * (nt & 3) + (g & 1)) * 4 + t];
+        else
+          b = __ldg(reinterpret_cast<const uint4*>(Vc + (32 * (nt >> 2) + 2 * (nt & 3)) * 32));
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           mma_bf16_16816(o[mt][nt], pa[mt][0], b.x, b.y);
@@ -490,6 +531,11 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, __nv_bfloa
 
 }  // namespace bya
 
+namespace bya {
+int xattn_tc_dispatch(cudaStream_t s, const void* q, int ldq, const void* K, const void* Vt, const float* w, void* out,
+                      int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames, float scale);   // xattn_tc.cu
+}
+
 using namespace bya;
 
 extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* K, const void* Vt, const float* w,
@@ -504,27 +550,47 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(K) |
        reinterpret_cast<uintptr_t>(Vt)) & 15)
     return BYA_ERR_ALIGN;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (tok_begin == 0 && tokens == total_tokens) {   // full clip, 1-2 characters: tensor-memory form (xattn_tc.cu)
+    const int r = xattn_tc_dispatch(s, q, ldq, K, Vt, w, out, ldo, tokens, heads, head_dim, chars, kv_frames, scale);
+    if (r != 1) return r;
+  }
   const int tpf = int(total_tokens / kv_frames);
   static int xa_hpg = -1;   // heads per block (tuning knob BYA_XA_HPG; default 4 at d = 64, 2 at d = 128)
   if (xa_hpg < 0) { const char* e = std::getenv("BYA_XA_HPG"); xa_hpg = e ? std::atoi(e) : 0; if (xa_hpg < 0) xa_hpg = 0; }
   const int hpg = xa_hpg ? xa_hpg : (head_dim == 64 ? 4 : 2);
   static int xa_pf = -1;    // K / V^T L1 prefetch of the next head (BYA_XA_PF: 0 off, 1 prefetch.global.L1, 2 sector-touching loads)
   if (xa_pf < 0) { const char* e = std::getenv("BYA_XA_PF"); xa_pf = e ? std::atoi(e) : 1; if (xa_pf < 0 || xa_pf > 2) xa_pf = 1; }
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const float sl2 = scale * 1.4426950408889634f;
-#define BYA_XA(D_, C_, MT_)                                                                                       \
+#define BYA_XA(D_, C_, MT_, BL_, ST_)                                                                             \
   do {                                                                                                            \
     dim3 grid((tpf + XA_WARPS * 16 * MT_ - 1) / (XA_WARPS * 16 * MT_), kv_frames, (heads + hpg - 1) / hpg);       \
-    xattn_kv32_kernel<D_, C_, MT_><<<grid, XA_WARPS * 32, 0, s>>>(                                                \
-        (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)K, (const __nv_bfloat16*)Vt, w, (__nv_bfloat16*)out,  \
-        ldo, heads, tpf, kv_frames, sl2, tok_begin, tokens, xa_pf);                                               \
+    constexpr int smem = XA_WARPS * 2 * 16 * MT_ * (D_ / 8) * 16 + (ST_ ? 2 * C_ * 2 * 4 * D_ * 16 : 0);          \
+    auto kern = xattn_kv32_kernel<D_, C_, MT_, BL_, ST_>;                                                         \
+    static bool attr = false;                                                                                     \
+    if (!attr) {                                                                                                  \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)           \
+        return BYA_ERR_CUDA;                                                                                      \
+      attr = true;                                                                                                \
+    }                                                                                                             \
+    kern<<<grid, XA_WARPS * 32, smem, s>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)K,                 \
+                                           (const __nv_bfloat16*)Vt, w, (__nv_bfloat16*)out, ldo, heads, tpf,     \
+                                           kv_frames, sl2, tok_begin, tokens, xa_pf);                             \
   } while (0)
-  if (head_dim == 64 && chars == 1) BYA_XA(64, 1, 2);
-  else if (head_dim == 64 && chars == 2) BYA_XA(64, 2, 2);
-  else if (head_dim == 64 && chars == 3) BYA_XA(64, 3, 2);
-  else if (head_dim == 128 && chars == 1) BYA_XA(128, 1, 1);
-  else if (head_dim == 128 && chars == 2) BYA_XA(128, 2, 1);
-  else if (head_dim == 128 && chars == 3) BYA_XA(128, 3, 1);
+  static int xa_var = -1;   // tuning knob BYA_XA_VAR: 0 K / V^T through L1, 1 staged in shared memory
+  if (xa_var < 0) { const char* e = std::getenv("BYA_XA_VAR"); xa_var = e ? std::atoi(e) : 0; }
+  if (head_dim == 64 && chars == 1) BYA_XA(64, 1, 2, 3, false);
+  else if (head_dim == 64 && chars == 2) {
+    if (xa_var == 1) BYA_XA(64, 2, 2, 3, true);
+    else BYA_XA(64, 2, 2, 3, false);
+  }
+  else if (head_dim == 64 && chars == 3) BYA_XA(64, 3, 2, 3, false);
+  else if (head_dim == 128 && chars == 1) BYA_XA(128, 1, 1, 3, false);
+  else if (head_dim == 128 && chars == 2) {
+    if (xa_var == 1) BYA_XA(128, 2, 1, 2, true);
+    else BYA_XA(128, 2, 1, 3, false);
+  }
+  else if (head_dim == 128 && chars == 3) BYA_XA(128, 3, 1, 3, false);
   else return BYA_ERR_SHAPE;
 #undef BYA_XA
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
