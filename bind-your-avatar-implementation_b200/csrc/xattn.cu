@@ -533,7 +533,8 @@ small_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, __nv_bfloa
 
 namespace bya {
 int xattn_tc_dispatch(cudaStream_t s, const void* q, int ldq, const void* K, const void* Vt, const float* w, void* out,
-                      int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames, float scale);   // xattn_tc.cu
+                      int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames, float scale,
+                      long long tok_begin, long long total_tokens);   // xattn_tc.cu
 }
 
 using namespace bya;
@@ -551,8 +552,9 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
        reinterpret_cast<uintptr_t>(Vt)) & 15)
     return BYA_ERR_ALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (tok_begin == 0 && tokens == total_tokens) {   // full clip, 1-2 characters: tensor-memory form (xattn_tc.cu)
-    const int r = xattn_tc_dispatch(s, q, ldq, K, Vt, w, out, ldo, tokens, heads, head_dim, chars, kv_frames, scale);
+  {   // 1-2 characters: tensor-memory form (xattn_tc.cu)
+    const int r = xattn_tc_dispatch(s, q, ldq, K, Vt, w, out, ldo, tokens, heads, head_dim, chars, kv_frames, scale,
+                                    tok_begin, total_tokens);
     if (r != 1) return r;
   }
   const int tpf = int(total_tokens / kv_frames);

@@ -15,9 +15,11 @@
 //   * O = sum_c (w_c P_c) V_c runs as tcgen05.mma with A = P from tensor memory and B = V^T_c (K-major, 64-byte rows,
 //     64B swizzle) accumulating over the characters — the routed blend of transformer.py:821-822 / :925-926 costs nothing;
 //   * the same four warps drain O (tcgen05.ld), round to bf16 and leave through a 64B-swizzled staging tile + TMA
-//     store, clipped at the frame boundary by a [frame][token][column] tensor map.
-// Full-clip calls with 1 or 2 characters take this path; sequence-parallel shards (a rank's rows start in the middle
-// of a frame) and 3 characters stay on the mma.sync kernel.  Same contract, same operand layouts (include/bya.h).
+//     store; warps whose 32 rows are not all valid (end of a frame, edges of a sequence-parallel shard) store per row.
+// The q / out tensor maps cover the rows THIS RANK holds; a tile's first row may be negative or run past the end (TMA
+// zero-fills / clips), so the same kernel — and the same per-row arithmetic, bit for bit — serves the whole clip and
+// sequence-parallel shards that start in the middle of a frame.  3 characters stay on the mma.sync kernel.
+// Same contract, same operand layouts (include/bya.h).
 #include "common.cuh"
 #include "../../include/bya.h"
 
@@ -57,7 +59,10 @@ struct XtSmem {
 
 struct XtArgs {
   const float* w;
-  int heads, tpf, kv_frames, hpg, three_d;
+  __nv_bfloat16* out;      // for the guarded stores of warps whose 32 rows are not all valid (frame end, shard edges)
+  long long tok_begin;     // this rank holds the tokens [tok_begin, tok_begin + tok_count) of the clip; q / w / out rows are local
+  int tok_count, ldo;
+  int heads, tpf, kv_frames, hpg;
   float scale_log2;
 };
 
@@ -107,6 +112,11 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
   const int h_begin = blockIdx.z * p.hpg, h_end = min(p.heads, h_begin + p.hpg);
   const int nh = h_end - h_begin;
   constexpr int WI = 4 * NWG;   // the issuing warp
+  // local row of the tile's first token: the q / out tensor maps cover THIS RANK's rows, and TMA zero-fills / clips rows
+  // outside them (negative or past the end), so a tile may hang over either edge of the shard
+  const long long local0_ll = (long long)frame * p.tpf + (long long)tile * 128 - p.tok_begin;
+  if (local0_ll + 128 <= 0 || local0_ll >= p.tok_count) return;   // no owned token in this tile (whole CTA)
+  const int local0 = int(local0_ll);
 
   if (warp == WI && lane == 0) {
     tma_prefetch_desc(&tmq);
@@ -143,8 +153,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         mbar_arrive_expect_tx(&full[st], L::kStage);
 #pragma unroll
         for (int kd = 0; kd < L::KD; ++kd) {
-          if (p.three_d) tma_load_3d(sQ + kd * L::kQBox, &tmq, &full[st], h * D + kd * 64, tile * 128, frame, kEvictFirst);
-          else tma_load_2d(sQ + kd * L::kQBox, &tmq, &full[st], h * D + kd * 64, tile * 128, kEvictFirst);
+          tma_load_2d(sQ + kd * L::kQBox, &tmq, &full[st], h * D + kd * 64, local0, kEvictFirst);
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -203,16 +212,18 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
     const int g = warp >> 2, q4 = warp & 3;
     const int r = q4 * 32 + lane;
     const int tok = tile * 128 + r;                               // within the frame
-    const bool valid = tok < p.tpf;
+    const int lrow = local0 + r;                                  // local row of q / w / out
+    // rows past the end of the frame hold the NEXT frame's tokens (wrong K / V), rows outside the shard are zero-filled
+    const bool valid = tok < p.tpf && lrow >= 0 && lrow < p.tok_count;
+    const bool warp_full = __all_sync(0xffffffffu, valid);        // all 32 rows valid: the warp's tile leaves by TMA
     float wt[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c)
-      wt[c] = valid ? (p.w ? p.w[(size_t(frame) * p.tpf + tok) * C + c] : 1.f) : 0.f;
+    for (int c = 0; c < C; ++c) wt[c] = valid ? (p.w ? p.w[size_t(lrow) * C + c] : 1.f) : 0.f;
     const uint32_t tS = tmem_base + g * Cfg::kWgCols + (uint32_t(q4 * 32) << 16);
     const uint32_t tO = tS + 64;
     uint8_t* stg = smem + L::kStgOffset + warp * 2048;
     const uint32_t stg_row = smem_u32(stg) + lane * 64;
-    const int row0 = tile * 128 + q4 * 32;
+    const int row0 = local0 + q4 * 32;
     const float sl2 = p.scale_log2;
     for (int i = g; i < nh; i += NWG) {
       const int h = h_begin + i;
@@ -265,6 +276,18 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(&o_free[g]);
         }
+        if (!warp_full) {   // frame end / shard edge: every valid row stores its own 64 bytes
+          if (valid) {
+            uint4* d = reinterpret_cast<uint4*>(p.out + size_t(lrow) * p.ldo + h * D + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              d[j] = make_uint4(pack_bf16x2(__uint_as_float(orr[8 * j]), __uint_as_float(orr[8 * j + 1])),
+                                pack_bf16x2(__uint_as_float(orr[8 * j + 2]), __uint_as_float(orr[8 * j + 3])),
+                                pack_bf16x2(__uint_as_float(orr[8 * j + 4]), __uint_as_float(orr[8 * j + 5])),
+                                pack_bf16x2(__uint_as_float(orr[8 * j + 6]), __uint_as_float(orr[8 * j + 7])));
+          }
+          continue;
+        }
         if (lane == 0) tma_store_wait_read<0>();   // the previous chunk's store has finished reading the staging tile
         __syncwarp();
 #pragma unroll
@@ -277,8 +300,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.three_d) tma_store_3d(&tmo, stg, h * D + ch * 32, row0, frame);
-          else tma_store_2d(&tmo, stg, h * D + ch * 32, row0);
+          tma_store_2d(&tmo, stg, h * D + ch * 32, row0);
           tma_store_commit();
         }
       }
@@ -292,16 +314,15 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__
 
 template <int D, int C>
 static int launch_xattn_tc(cudaStream_t s, const void* q, int ldq, const void* K, const void* Vt, const float* w, void* out,
-                           int ldo, int tokens, int heads, int kv_frames, float scale, int hpg) {
+                           int ldo, int tokens, int heads, int kv_frames, float scale, long long tok_begin,
+                           long long total_tokens, int hpg) {
   using L = XtSmem<D, C>;
-  const int tpf = tokens / kv_frames;
+  const int tpf = int(total_tokens / kv_frames);
   const int G = C * kv_frames;
   CUtensorMap tmq, tmk, tmv, tmo;
-  int rc = bya_host::encode_tmap_bf16(&tmq, q, uint64_t(heads) * D, tpf, uint64_t(ldq) * 2, 64, 128, kv_frames,
-                                      uint64_t(tpf) * ldq * 2);
+  int rc = bya_host::encode_tmap_bf16(&tmq, q, uint64_t(heads) * D, tokens, uint64_t(ldq) * 2, 64, 128);
   if (rc) return rc;
-  rc = bya_host::encode_tmap_bf16(&tmo, out, uint64_t(heads) * D, tpf, uint64_t(ldo) * 2, 32, 32, kv_frames,
-                                  uint64_t(tpf) * ldo * 2);
+  rc = bya_host::encode_tmap_bf16(&tmo, out, uint64_t(heads) * D, tokens, uint64_t(ldo) * 2, 32, 32);
   if (rc) return rc;
   rc = bya_host::encode_tmap_bf16(&tmk, K, D, uint64_t(G) * heads * 32, uint64_t(D) * 2, 64, 32);
   if (rc) return rc;
@@ -315,17 +336,20 @@ static int launch_xattn_tc(cudaStream_t s, const void* q, int ldq, const void* K
   }
   XtArgs a;
   a.w = w;
-  a.heads = heads, a.tpf = tpf, a.kv_frames = kv_frames, a.hpg = hpg, a.three_d = kv_frames > 1;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.tok_begin = tok_begin, a.tok_count = tokens, a.ldo = ldo;
+  a.heads = heads, a.tpf = tpf, a.kv_frames = kv_frames, a.hpg = hpg;
   a.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((tpf + 127) / 128, kv_frames, (heads + hpg - 1) / hpg);
   kern<<<grid, XtCfg<D>::kThreads, L::kTotal, s>>>(tmq, tmk, tmv, tmo, a);
   return cudaGetLastError() == cudaSuccess ? BYA_OK : BYA_ERR_CUDA;
 }
 
-// Called by bya_xattn_kv32 (xattn.cu) for full-clip calls with 1 or 2 characters; returns 1 when the call is not for
-// this kernel (the mma.sync form then runs), BYA_OK / an error code otherwise.
+// Called by bya_xattn_kv32 (xattn.cu) for calls with 1 or 2 characters; returns 1 when the call is not for this kernel
+// (the mma.sync form then runs), BYA_OK / an error code otherwise.
 int xattn_tc_dispatch(cudaStream_t s, const void* q, int ldq, const void* K, const void* Vt, const float* w, void* out,
-                      int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames, float scale) {
+                      int ldo, int tokens, int heads, int head_dim, int chars, int kv_frames, float scale,
+                      long long tok_begin, long long total_tokens) {
   static int on = -1, hpg_env = 0;
   if (on < 0) {
     const char* e = std::getenv("BYA_XA_TC");
@@ -333,12 +357,15 @@ int xattn_tc_dispatch(cudaStream_t s, const void* q, int ldq, const void* K, con
     const char* g = std::getenv("BYA_XA_TC_HPG");
     hpg_env = g ? std::atoi(g) : 0;
   }
-  if (!on || chars > 2 || tokens % kv_frames) return 1;
+  if (!on || chars > 2) return 1;
   const int hpg = hpg_env > 0 ? hpg_env : (head_dim == 64 ? 8 : 4);
-  if (head_dim == 64 && chars == 1) return launch_xattn_tc<64, 1>(s, q, ldq, K, Vt, w, out, ldo, tokens, heads, kv_frames, scale, hpg);
-  if (head_dim == 64 && chars == 2) return launch_xattn_tc<64, 2>(s, q, ldq, K, Vt, w, out, ldo, tokens, heads, kv_frames, scale, hpg);
-  if (head_dim == 128 && chars == 1) return launch_xattn_tc<128, 1>(s, q, ldq, K, Vt, w, out, ldo, tokens, heads, kv_frames, scale, hpg);
-  if (head_dim == 128 && chars == 2) return launch_xattn_tc<128, 2>(s, q, ldq, K, Vt, w, out, ldo, tokens, heads, kv_frames, scale, hpg);
+#define BYA_XT(D_, C_) \
+  return launch_xattn_tc<D_, C_>(s, q, ldq, K, Vt, w, out, ldo, tokens, heads, kv_frames, scale, tok_begin, total_tokens, hpg)
+  if (head_dim == 64 && chars == 1) BYA_XT(64, 1);
+  if (head_dim == 64 && chars == 2) BYA_XT(64, 2);
+  if (head_dim == 128 && chars == 1) BYA_XT(128, 1);
+  if (head_dim == 128 && chars == 2) BYA_XT(128, 2);
+#undef BYA_XT
   return 1;
 }
 

@@ -457,6 +457,32 @@ def test_routed_cross_attention(ops, heads, hd, chars, kvf, tokens):
     assert rel(out, ref) < 1.5e-2
 
 
+@pytest.mark.parametrize("heads,hd,chars,kvf,tpf,shards", [(48, 64, 2, 13, 150, 4), (16, 128, 2, 1, 1350, 8), (6, 64, 3, 5, 77, 2),
+                                                          (4, 64, 1, 3, 200, 3)])
+def test_routed_cross_attention_on_token_shards(ops, heads, hd, chars, kvf, tpf, shards):
+    """Sequence-parallel use (`tok_begin`, `total_tokens`): a rank passes only its rows, which start and end in the middle
+    of frames.  Every shard must reproduce its rows of the full-clip call BIT FOR BIT (the multi-GPU step is compared with
+    the single-GPU step that way), and must not touch a row outside the shard."""
+    torch.manual_seed(11)
+    tokens = kvf * tpf
+    q = rnd(tokens, heads * hd)
+    K = rnd(chars * kvf, heads, 32, hd)
+    Vt = rnd(chars * kvf, heads, hd, 32)
+    w = torch.rand(tokens, chars, device=dev)
+    w[::3, 0] = 0.0                      # hard-routed tokens: a character with weight 0 contributes nothing
+    full = torch.empty_like(q)
+    ops.xattn_kv32(q, K, Vt, w, full, heads, hd, chars, kvf, hd ** -0.5)
+    bounds = [round(i * tokens / shards) for i in range(shards + 1)]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        guard = 5
+        buf = torch.full((b - a + 2 * guard, heads * hd), 7.0, device=dev, dtype=torch.bfloat16)
+        part = buf[guard:guard + b - a]
+        ops.xattn_kv32(q[a:b].contiguous(), K, Vt, w[a:b].contiguous(), part, heads, hd, chars, kvf, hd ** -0.5,
+                       tok_begin=a, total_tokens=tokens)
+        assert torch.equal(part, full[a:b])
+        assert bool((buf[:guard] == 7.0).all()) and bool((buf[guard + b - a:] == 7.0).all())
+
+
 def test_router_small_attention_and_head(ops):
     torch.manual_seed(10)
     C, Fr, hw, H = 2, 13, 24, 8
