@@ -80,7 +80,10 @@ BYA_DEVICE void xa_add2(float& a0, float& a1, float b0, float b1) { // a = a + b
 //   * MT = 2 token tiles per warp at d = 64 share every K / V^T fragment (L1 wavefronts per token halved);
 //   * the softmax runs on ex2.approx / rcp.approx and packed f32x2 arithmetic (the kernel is issue-bound: ~1 600 warp
 //     instructions per 32 tokens x head before, the MMAs are 128 of them).
-// pf_mode: 0 no K / V^T prefetch, 1 prefetch.global.L1, 2 sector-touching loads.
+// pf_mode: 0 no K / V^T prefetch, 1 prefetch.global.L1 (default; measured 97.7 -> 90.0 us at the audio shape).
+// STAGE: K / V^T of the block's current and next head staged in shared memory by cp.async instead (one block barrier per
+// head): 82 us at the audio shape — kept as BYA_XA_VAR=1 for the 2-character shapes; the default path for 1-2 characters is
+// the tensor-memory kernel (xattn_tc.cu), this one serves 3 characters and BYA_XA_TC=0.
 template <int D, int C, int MT, int XA_BLOCKS, bool STAGE>
 __global__ void __launch_bounds__(XA_WARPS * 32, XA_BLOCKS)
 xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ K,
@@ -145,13 +148,7 @@ xattn_kv32_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
       const int which = i / LPT, ln = i - which * LPT;
       const size_t grp = (size_t(which >> 1) * kv_frames + frame) * heads + h;
       const char* p = reinterpret_cast<const char*>(((which & 1) ? Vt : K) + grp * 32 * D) + ln * 128;
-      if (pf_mode == 1) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-      } else {
-        uint32_t d0, d1, d2, d3;   // one word per 32-byte sector
-        asm volatile("ld.global.nc.b32 %0, [%4];\n\tld.global.nc.b32 %1, [%4+32];\n\tld.global.nc.b32 %2, [%4+64];\n\t"
-                     "ld.global.nc.b32 %3, [%4+96];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "l"(p));
-      }
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
     }
   };
   // ---- q rows of head h -> landing buffer b (16-byte cp.async, chunk ^ 4 on odd rows keeps the fragment reads conflict-free)
@@ -561,8 +558,8 @@ extern "C" int bya_xattn_kv32(void* stream, const void* q, int ldq, const void* 
   static int xa_hpg = -1;   // heads per block (tuning knob BYA_XA_HPG; default 4 at d = 64, 2 at d = 128)
   if (xa_hpg < 0) { const char* e = std::getenv("BYA_XA_HPG"); xa_hpg = e ? std::atoi(e) : 0; if (xa_hpg < 0) xa_hpg = 0; }
   const int hpg = xa_hpg ? xa_hpg : (head_dim == 64 ? 4 : 2);
-  static int xa_pf = -1;    // K / V^T L1 prefetch of the next head (BYA_XA_PF: 0 off, 1 prefetch.global.L1, 2 sector-touching loads)
-  if (xa_pf < 0) { const char* e = std::getenv("BYA_XA_PF"); xa_pf = e ? std::atoi(e) : 1; if (xa_pf < 0 || xa_pf > 2) xa_pf = 1; }
+  static int xa_pf = -1;    // K / V^T L1 prefetch of the next head (BYA_XA_PF: 0 off, 1 prefetch.global.L1)
+  if (xa_pf < 0) { const char* e = std::getenv("BYA_XA_PF"); xa_pf = e ? std::atoi(e) : 1; if (xa_pf < 0 || xa_pf > 1) xa_pf = 1; }
   const float sl2 = scale * 1.4426950408889634f;
 #define BYA_XA(D_, C_, MT_, BL_, ST_)                                                                             \
   do {                                                                                                            \

@@ -483,6 +483,24 @@ def test_routed_cross_attention_on_token_shards(ops, heads, hd, chars, kvf, tpf,
         assert bool((buf[:guard] == 7.0).all()) and bool((buf[guard + b - a:] == 7.0).all())
 
 
+@pytest.mark.parametrize("env", [{"BYA_XA_TC": "0"}, {"BYA_XA_TC": "0", "BYA_XA_VAR": "1"}])
+def test_routed_cross_attention_mma_sync_forms(env):
+    """The mma.sync forms of the cross-attention (3 characters use them by default; BYA_XA_TC=0 forces them for 1-2
+    characters, BYA_XA_VAR=1 stages K / V^T in shared memory) against fp32 torch at the probe's shapes.  The knobs are read
+    once per process, hence the subprocess."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_debug_xattn_tc.py")], capture_output=True, text=True,
+                       env={**os.environ, **env}, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if "rel max err" in l]
+    errs = [float(l.split("rel max err")[1].split()[0]) for l in lines]
+    nans = [int(l.split(" nan ")[1].split("/")[0]) for l in lines]
+    assert len(errs) == 7 and max(errs) < 1.5e-2 and sum(nans) == 0, r.stdout
+
+
 def test_router_small_attention_and_head(ops):
     torch.manual_seed(10)
     C, Fr, hw, H = 2, 13, 24, 8
