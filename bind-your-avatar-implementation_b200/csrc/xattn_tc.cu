@@ -6,9 +6,9 @@
 // loads, quad shuffles for every row maximum / row sum, 128 HMMAs — and plateaus at 0.35-0.4 of the HBM roofline however
 // its operands are staged (ncu: no pipe above 35 %, the warps wait on each other's fixed latencies).  Here a CTA owns a
 // 128-token tile of one frame and walks the heads of its group:
-//   * one elected thread moves everything with TMA: the q tile (128 x d, zero-filled past the end of the frame), the
-//     32 keys of EVERY character stacked into one K operand (32 C rows) and each character's V^T (d rows of 32 keys),
-//     double-buffered one head ahead;
+//   * one elected thread moves everything with TMA: the q tile (128 x d; rows outside this rank's rows are zero-filled,
+//     rows past the end of the frame belong to the next frame and are computed but never stored), the 32 keys of EVERY
+//     character stacked into one K operand (32 C rows) and each character's V^T (d rows of 32 keys), 2-3 stages ahead;
 //   * S = Q K^T is ONE tcgen05.mma chain (M = 128, N = 32 C) into tensor memory; a softmax thread owns a token ROW:
 //     it pulls its 32 C scores with tcgen05.ld, takes max / exp2 / sum per character without a single shuffle, folds
 //     w_c / sum_c into the probabilities and writes them back to tensor memory as packed bf16;
